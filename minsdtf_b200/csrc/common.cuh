@@ -1,0 +1,119 @@
+// common.cuh — error handling, tensor views and the TMA tensor-map encoder shared by all launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cudaTypedefs.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace sdtf {
+
+using bf16 = __nv_bfloat16;
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define SDTF_CUDA(expr)                                                                          \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess)                                                                       \
+      throw ::sdtf::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +   \
+                          __FILE__ + ":" + std::to_string(__LINE__));                            \
+  } while (0)
+
+#define SDTF_CHECK(cond, msg)                                                                    \
+  do {                                                                                           \
+    if (!(cond))                                                                                 \
+      throw ::sdtf::Error(std::string("check failed: ") + #cond + " — " + (msg) + " at " +       \
+                          __FILE__ + ":" + std::to_string(__LINE__));                            \
+  } while (0)
+
+// NHWC bf16 activation view.  `ld` is the element distance between consecutive pixels, so a view can be a
+// channel slice [c0, c0+C) of a wider buffer (that is how channel concats are laid out: the producers of
+// the two halves write straight into one buffer, see unet.cu).
+struct View {
+  bf16* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  long long ld = 0;
+  long long pixels() const { return (long long)B * H * W; }
+  View slice(int c0, int c) const {
+    View v = *this;
+    v.p = p + c0;
+    v.C = c;
+    return v;
+  }
+  // same memory seen as a [1][1][B*H*W] token matrix
+  View tokens() const {
+    View v = *this;
+    v.W = B * H * W;
+    v.H = 1;
+    v.B = 1;
+    return v;
+  }
+};
+
+inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SDTF_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    SDTF_CHECK(p != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map, 128-byte swizzle, zero fill out of bounds.  dims/box/estr are innermost-first;
+// strides_bytes[i] is the byte stride of dimension i+1.
+inline CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                  const uint32_t* box, const uint32_t* estr) {
+  CUtensorMap m;
+  SDTF_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
+  for (int i = 0; i + 1 < rank; ++i)
+    SDTF_CHECK(strides_bytes[i] % 16 == 0, "TMA strides must be multiples of 16 bytes");
+  CUresult r = tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                                    reinterpret_cast<const cuuint64_t*>(dims),
+                                    reinterpret_cast<const cuuint64_t*>(strides_bytes),
+                                    reinterpret_cast<const cuuint32_t*>(box),
+                                    reinterpret_cast<const cuuint32_t*>(estr), CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string s = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") rank " + std::to_string(rank);
+    for (int i = 0; i < rank; ++i)
+      s += " d" + std::to_string(i) + "=" + std::to_string(dims[i]) + "/box" + std::to_string(box[i]) + "/es" +
+           std::to_string(estr[i]);
+    for (int i = 0; i + 1 < rank; ++i) s += " s" + std::to_string(i) + "=" + std::to_string(strides_bytes[i]);
+    throw Error(s);
+  }
+  return m;
+}
+
+// activation map over an NHWC view: dims (C, W, H, B); box (64, bw*stride, bh*stride, bn) with element
+// strides (1, stride, stride, 1) => exactly bw x bh x bn pixels x 64 channels = 16 KB per box.
+inline CUtensorMap make_act_tmap(const View& v, int bw, int bh, int bn, int stride) {
+  uint64_t dims[4] = {(uint64_t)v.C, (uint64_t)v.W, (uint64_t)v.H, (uint64_t)v.B};
+  uint64_t strides[3] = {(uint64_t)v.ld * 2, (uint64_t)v.W * v.ld * 2, (uint64_t)v.H * v.W * v.ld * 2};
+  uint32_t box[4] = {64, (uint32_t)(bw * stride), (uint32_t)(bh * stride), (uint32_t)bn};
+  uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+  return make_tmap_bf16(v.p, 4, dims, strides, box, es);
+}
+
+// packed weight map [taps][N][K]: dims (K, N, taps), box (64, BN, 1)
+inline CUtensorMap make_weight_tmap(const bf16* w, int K, int N, int taps, int BN) {
+  uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)taps};
+  uint64_t strides[2] = {(uint64_t)K * 2, (uint64_t)N * K * 2};
+  uint32_t box[3] = {64, (uint32_t)BN, 1};
+  uint32_t es[3] = {1, 1, 1};
+  return make_tmap_bf16(w, 3, dims, strides, box, es);
+}
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+}  // namespace sdtf

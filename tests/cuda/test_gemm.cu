@@ -1,0 +1,268 @@
+// Standalone GPU check + micro-benchmark of conv_gemm_kernel against a naive CUDA reference.
+// Build:  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -I minsdtf_b200/csrc \
+//              tests/cuda/test_gemm.cu -o build/test_gemm
+// Run:    build/test_gemm [bench]
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "gemm_host.cuh"
+
+using namespace sdtf;
+
+struct Case {
+  const char* name;
+  int B, H, W, C0, C1, N, kh, kw, stride, pad_t, pad_l, outH, outW;
+  bool bias, temb, res, out_fp32;
+  int act;
+  int force_bn;
+  int ld_extra;  // extra channels of pixel stride (tests strided / sliced views)
+};
+
+__global__ void ref_conv(const bf16* a0, long long ld0, int C0, const bf16* a1, long long ld1, int C1, const bf16* w,
+                         int K, int N, int kh, int kw, int stride, int pad_t, int pad_l, int B, int H, int W, int outH,
+                         int outW, const float* bias, const float* temb, int temb_ld, const bf16* res, long long res_ld,
+                         float* out /* [pix][Nout] */, int act, int geglu_half) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int Nout = act == ACT_GEGLU ? N / 2 : N;
+  long long total = (long long)B * outH * outW * Nout;
+  if (idx >= total) return;
+  int n = idx % Nout;
+  long long pix = idx / Nout;
+  int ox = pix % outW;
+  int oy = (pix / outW) % outH;
+  int b = pix / ((long long)outW * outH);
+  auto dot = [&](int row) {
+    float acc = 0.f;
+    for (int r = 0; r < kh; ++r)
+      for (int s = 0; s < kw; ++s) {
+        int iy = oy * stride + r - pad_t, ix = ox * stride + s - pad_l;
+        if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;
+        long long ip = ((long long)b * H + iy) * W + ix;
+        const bf16* wr = w + ((long long)(r * kw + s) * N + row) * K;
+        for (int k = 0; k < C0; ++k) acc += __bfloat162float(a0[ip * ld0 + k]) * __bfloat162float(wr[k]);
+        for (int k = 0; k < C1; ++k) acc += __bfloat162float(a1[ip * ld1 + k]) * __bfloat162float(wr[C0 + k]);
+      }
+    return acc;
+  };
+  float v;
+  if (act == ACT_GEGLU) {
+    int tile = n / geglu_half, j = n % geglu_half;
+    int rv = tile * 2 * geglu_half + j, rg = rv + geglu_half;
+    float val = dot(rv) + (bias ? bias[rv] : 0.f);
+    float g = dot(rg) + (bias ? bias[rg] : 0.f);
+    v = val * 0.5f * g * (1.f + tanhf(g * 0.7978845608f * (1.f + 0.044715f * g * g)));
+  } else {
+    v = dot(n);
+    if (bias) v += bias[n];
+    if (temb) v += temb[(long long)b * temb_ld + n];
+    if (res) v += __bfloat162float(res[pix * res_ld + n]);
+    if (act == ACT_SILU) v = v / (1.f + expf(-v));
+  }
+  out[pix * Nout + n] = v;
+}
+
+static uint32_t rng_state = 12345;
+static float frand() {
+  rng_state = rng_state * 1664525u + 1013904223u;
+  return ((rng_state >> 8) & 0xFFFF) / 32768.f - 1.f;
+}
+
+template <class T>
+T* dalloc(size_t n) {
+  T* p;
+  SDTF_CUDA(cudaMalloc(&p, n * sizeof(T)));
+  return p;
+}
+static bf16* upload_bf16(const std::vector<float>& h) {
+  std::vector<bf16> t(h.size());
+  for (size_t i = 0; i < h.size(); ++i) t[i] = __float2bfloat16(h[i]);
+  bf16* d = dalloc<bf16>(h.size());
+  SDTF_CUDA(cudaMemcpy(d, t.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  return d;
+}
+static float* upload_f32(const std::vector<float>& h) {
+  float* d = dalloc<float>(h.size());
+  SDTF_CUDA(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  return d;
+}
+
+static bool run_case(const Case& c, bool bench) {
+  const int K = c.C0 + c.C1;
+  const int Kp = (K + 7) / 8 * 8;
+  const long long ipix = (long long)c.B * c.H * c.W, opix = (long long)c.B * c.outH * c.outW;
+  const long long ld0 = c.C0 + c.ld_extra, ld1 = c.C1 + c.ld_extra;
+  std::vector<float> h;
+  h.resize(ipix * ld0);
+  for (auto& x : h) x = frand();
+  bf16* a0 = upload_bf16(h);
+  bf16* a1 = nullptr;
+  if (c.C1) {
+    h.resize(ipix * ld1);
+    for (auto& x : h) x = frand();
+    a1 = upload_bf16(h);
+  }
+  const int taps = c.kh * c.kw;
+  h.assign((size_t)taps * c.N * Kp, 0.f);
+  const float ws = 1.f / sqrtf((float)K * taps);
+  for (int t = 0; t < taps; ++t)
+    for (int n = 0; n < c.N; ++n)
+      for (int k = 0; k < K; ++k) h[((size_t)t * c.N + n) * Kp + k] = frand() * ws * 1.7f;
+  bf16* w = upload_bf16(h);
+  float* bias = nullptr;
+  if (c.bias) {
+    h.resize(c.N);
+    for (auto& x : h) x = frand();
+    bias = upload_f32(h);
+  }
+  const int Nout = c.act == ACT_GEGLU ? c.N / 2 : c.N;
+  float* temb = nullptr;
+  if (c.temb) {
+    h.resize((size_t)c.B * Nout);
+    for (auto& x : h) x = frand();
+    temb = upload_f32(h);
+  }
+  const long long out_ld = Nout + c.ld_extra;
+  bf16* res = nullptr;
+  if (c.res) {
+    h.resize(opix * out_ld);
+    for (auto& x : h) x = frand();
+    res = upload_bf16(h);
+  }
+  void* out = c.out_fp32 ? (void*)dalloc<float>(opix * out_ld) : (void*)dalloc<bf16>(opix * out_ld);
+  SDTF_CUDA(cudaMemset(out, 0, opix * out_ld * (c.out_fp32 ? 4 : 2)));
+  float* ref = dalloc<float>(opix * Nout);
+
+  PackedWeight pw;
+  pw.w = w; pw.bias = bias; pw.K = Kp; pw.N = c.N; pw.kh = c.kh; pw.kw = c.kw;
+  pw.geglu_half = c.act == ACT_GEGLU ? 80 : 0;
+  ConvArgs a;
+  a.a0 = View{a0, c.B, c.H, c.W, c.C0, ld0};
+  if (c.C1) a.a1 = View{a1, c.B, c.H, c.W, c.C1, ld1};
+  a.w = &pw; a.stride = c.stride; a.pad_t = c.pad_t; a.pad_l = c.pad_l; a.outH = c.outH; a.outW = c.outW;
+  a.temb = temb; a.temb_ld = Nout; a.res = res; a.res_ld = out_ld; a.out = out; a.out_ld = out_ld;
+  a.out_fp32 = c.out_fp32; a.act = c.act; a.force_bn = c.force_bn;
+
+  launch_conv(0, a);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("CASE %-28s  CUDA ERROR: %s\n", c.name, cudaGetErrorString(e));
+    exit(3);
+  }
+  bool ok = true;
+  if (!bench || opix * Nout * (long long)K * taps < 4e11) {
+    long long total = opix * Nout;
+    ref_conv<<<(unsigned)((total + 255) / 256), 256>>>(a0, ld0, c.C0, a1, ld1, c.C1, w, Kp, c.N, c.kh, c.kw, c.stride,
+                                                       c.pad_t, c.pad_l, c.B, c.H, c.W, c.outH, c.outW, bias, temb,
+                                                       Nout, res, out_ld, ref, c.act, pw.geglu_half);
+    SDTF_CUDA(cudaDeviceSynchronize());
+    std::vector<float> hr(opix * Nout);
+    SDTF_CUDA(cudaMemcpy(hr.data(), ref, hr.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> ho(opix * out_ld);
+    if (c.out_fp32) {
+      SDTF_CUDA(cudaMemcpy(ho.data(), out, ho.size() * 4, cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<bf16> t(ho.size());
+      SDTF_CUDA(cudaMemcpy(t.data(), out, t.size() * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < t.size(); ++i) ho[i] = __bfloat162float(t[i]);
+    }
+    double max_err = 0, max_ref = 0;
+    long long bad = 0, first_bad = -1;
+    for (long long p = 0; p < opix; ++p)
+      for (int n = 0; n < Nout; ++n) {
+        float r = hr[p * Nout + n], o = ho[p * out_ld + n];
+        double err = fabs((double)r - o);
+        double tol = (c.out_fp32 ? 2e-3 : 1e-2) * (1.0 + fabs(r));
+        if (!(err <= tol)) {
+          if (first_bad < 0) first_bad = p * Nout + n;
+          ++bad;
+        }
+        if (err > max_err) max_err = err;
+        if (fabs(r) > max_ref) max_ref = fabs(r);
+      }
+    // untouched padding columns must stay zero
+    long long pad_bad = 0;
+    for (long long p = 0; p < opix; ++p)
+      for (int n = Nout; n < out_ld; ++n)
+        if (ho[p * out_ld + n] != 0.f) ++pad_bad;
+    ok = bad == 0 && pad_bad == 0;
+    printf("CASE %-28s  %s  max_err %.4g (max_ref %.3g) bad %lld pad_bad %lld", c.name, ok ? "OK  " : "FAIL", max_err,
+           max_ref, bad, pad_bad);
+    if (first_bad >= 0)
+      printf(" first_bad pix %lld n %lld ref %.4f got %.4f", first_bad / Nout, first_bad % Nout, hr[first_bad],
+             ho[(first_bad / Nout) * out_ld + first_bad % Nout]);
+    printf("\n");
+  }
+  if (bench) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) launch_conv(0, a);
+    cudaEventRecord(e0);
+    const int reps = 20;
+    for (int i = 0; i < reps; ++i) launch_conv(0, a);
+    cudaEventRecord(e1);
+    SDTF_CUDA(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= reps;
+    double flop = 2.0 * opix * c.N * (double)K * taps;
+    printf("BENCH %-27s  %.3f ms  %.1f TFLOP/s\n", c.name, ms, flop / ms * 1e-9);
+  }
+  cudaFree(a0); cudaFree(a1); cudaFree(w); cudaFree(bias); cudaFree(temb); cudaFree(res); cudaFree(out); cudaFree(ref);
+  fflush(stdout);
+  return ok;
+}
+
+int main(int argc, char** argv) {
+  bool bench = argc > 1 && !strcmp(argv[1], "bench");
+  std::vector<Case> cases = {
+      // name                      B  H   W   C0   C1   N   kh kw s pt pl oH oW  bias temb res  f32  act  bn ldx
+      {"linear_64x64x16",          1, 1, 128,  64,   0,  16, 1, 1, 1, 0, 0, 1, 128, false, false, false, true, ACT_NONE, 16, 0},
+      {"linear_k128_n64",          1, 1, 128, 128,   0,  64, 1, 1, 1, 0, 0, 1, 128, false, false, false, true, ACT_NONE, 0, 0},
+      {"linear_ragged_m300",       1, 1, 300, 320,   0, 320, 1, 1, 1, 0, 0, 1, 300, true, false, false, false, ACT_NONE, 0, 0},
+      {"linear_bn80",              1, 1, 300, 320,   0, 320, 1, 1, 1, 0, 0, 1, 300, true, false, true, false, ACT_NONE, 80, 0},
+      {"linear_n1280_res",         1, 1, 512, 640,   0, 1280, 1, 1, 1, 0, 0, 1, 512, true, false, true, false, ACT_NONE, 0, 0},
+      {"linear_geglu",             1, 1, 256, 320,   0, 2560, 1, 1, 1, 0, 0, 1, 256, true, false, false, false, ACT_GEGLU, 0, 0},
+      {"conv1x1_concat_slice",     2, 8, 8, 128,  64, 128, 1, 1, 1, 0, 0, 8, 8, true, false, false, false, ACT_NONE, 0, 64},
+      {"conv3x3_16x16",            2, 16, 16, 64,   0,  64, 3, 3, 1, 1, 1, 16, 16, true, false, false, false, ACT_NONE, 0, 0},
+      {"conv3x3_temb_res",         2, 32, 32, 320,  0, 320, 3, 3, 1, 1, 1, 32, 32, true, true, true, false, ACT_NONE, 0, 0},
+      {"conv3x3_concat",           2, 16, 16, 128, 64, 160, 3, 3, 1, 1, 1, 16, 16, true, true, false, false, ACT_NONE, 0, 0},
+      {"conv3x3_in4_pad8",         2, 64, 64,   8,  0, 320, 3, 3, 1, 1, 1, 64, 64, true, false, false, false, ACT_NONE, 0, 0},
+      {"conv3x3_out4_f32",         2, 64, 64, 320,  0,   4, 3, 3, 1, 1, 1, 64, 64, true, false, false, true, ACT_NONE, 0, 0},
+      {"conv3x3_s2_pad1",          2, 32, 32, 64,   0,  64, 3, 3, 2, 1, 1, 16, 16, true, false, false, false, ACT_NONE, 0, 0},
+      {"conv3x3_s2_pad0(asym)",    1, 32, 32, 128,  0, 128, 3, 3, 2, 0, 0, 16, 16, true, false, false, false, ACT_NONE, 0, 0},
+      {"conv3x3_s2_8x8",           2, 16, 16, 64,   0,  96, 3, 3, 2, 1, 1, 8, 8, true, false, false, false, ACT_SILU, 0, 0},
+      {"conv3x3_96x96",            1, 96, 96, 64,   0,  64, 3, 3, 1, 1, 1, 96, 96, true, false, false, false, ACT_NONE, 0, 0},
+      {"conv3x3_12x12_b3",         3, 12, 12, 64,   0,  64, 3, 3, 1, 1, 1, 12, 12, true, false, false, false, ACT_NONE, 0, 0},
+      {"conv3x3_c16_silu",         1, 64, 64,  16,  0,  32, 3, 3, 1, 1, 1, 64, 64, true, false, false, false, ACT_SILU, 0, 0},
+  };
+  std::vector<Case> bench_cases = {
+      {"b16_conv3x3_64_320",      16, 64, 64, 320,  0, 320, 3, 3, 1, 1, 1, 64, 64, true, true, false, false, ACT_NONE, 0, 0},
+      {"b16_conv3x3_32_640",      16, 32, 32, 640,  0, 640, 3, 3, 1, 1, 1, 32, 32, true, true, false, false, ACT_NONE, 0, 0},
+      {"b16_conv3x3_16_1280",     16, 16, 16, 1280, 0, 1280, 3, 3, 1, 1, 1, 16, 16, true, true, false, false, ACT_NONE, 0, 0},
+      {"b16_conv3x3_8_1280",      16, 8, 8, 1280,   0, 1280, 3, 3, 1, 1, 1, 8, 8, true, true, false, false, ACT_NONE, 0, 0},
+      {"b16_conv3x3_64_960cat",   16, 64, 64, 640, 320, 320, 3, 3, 1, 1, 1, 64, 64, true, true, false, false, ACT_NONE, 0, 0},
+      {"b16_geglu_4096x320",       1, 1, 65536, 320, 0, 2560, 1, 1, 1, 0, 0, 1, 65536, true, false, false, false, ACT_GEGLU, 0, 0},
+      {"b16_ff2_4096x1280",        1, 1, 65536, 1280, 0, 320, 1, 1, 1, 0, 0, 1, 65536, true, false, true, false, ACT_NONE, 0, 0},
+      {"b16_linear_1024x640",      1, 1, 16384, 640, 0, 640, 1, 1, 1, 0, 0, 1, 16384, true, false, true, false, ACT_NONE, 0, 0},
+      {"b2_conv3x3_64_320",        2, 64, 64, 320,  0, 320, 3, 3, 1, 1, 1, 64, 64, true, true, false, false, ACT_NONE, 0, 0},
+      {"b2_conv3x3_16_1280",       2, 16, 16, 1280, 0, 1280, 3, 3, 1, 1, 1, 16, 16, true, true, false, false, ACT_NONE, 0, 0},
+      {"vae_b4_conv3x3_512_128",   4, 512, 512, 128, 0, 128, 3, 3, 1, 1, 1, 512, 512, true, false, false, false, ACT_NONE, 0, 0},
+      {"vae_b4_conv3x3_256_256",   4, 256, 256, 256, 0, 256, 3, 3, 1, 1, 1, 256, 256, true, false, false, false, ACT_NONE, 0, 0},
+  };
+  int fails = 0;
+  try {
+    for (auto& c : cases) fails += run_case(c, false) ? 0 : 1;
+    if (bench)
+      for (auto& c : bench_cases) fails += run_case(c, true) ? 0 : 1;
+  } catch (const std::exception& e) {
+    printf("EXCEPTION: %s\n", e.what());
+    return 2;
+  }
+  printf("%s (%d failing)\n", fails ? "SOME CASES FAILED" : "ALL CASES PASSED", fails);
+  return fails ? 1 : 0;
+}
