@@ -1,0 +1,303 @@
+// attn.cuh — flash-style multi-head attention on tcgen05 for the SpatialTransformer blocks
+// (reference: diffusion_model.py:99-129 CrossAttention — softmax(Q K^T * d^-1/2) V, 8 heads, never
+// materialising the (B, 8, N, N) score tensor the reference builds at :123-126).
+//
+// One CTA = 128 query rows of one (batch, head).  Per 128-key tile:
+//   S = Q K^T        tcgen05.mma  M=128, N=keys(<=128), K=d     -> TMEM columns [0,128)
+//   online softmax   one thread per query row: tcgen05.ld S, running max / sum in fp32 registers,
+//                    P = exp2(S*scale - m) written as bf16 into 128B-swizzled smem (the A operand of PV)
+//   O (+)= P V       tcgen05.mma  M=128, N=d, K=keys; V is read straight from its [key][d] layout as an
+//                    MN-major B operand, O accumulates in TMEM columns [128, 128+d) and is rescaled in
+//                    place (tcgen05.ld / st) when the running max moves.
+// Q/K/V tiles arrive by TMA (3-D maps: column, token, batch) so ragged key counts (77-token context)
+// are zero-filled by the hardware and masked in the softmax.
+#pragma once
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace sdtf {
+
+struct AttnParams {
+  int Nq, Nk;        // queries / keys per batch element
+  int d;             // true head size (scale = d^-1/2, output columns per head)
+  int dstride;       // column distance between heads in the Q/K/V matrices (64 for d=40: zero padded)
+  float scale_log2;  // d^-1/2 * log2(e)
+  bf16* out;         // [B*Nq][ldo], head h at column h*d
+  long long ldo;
+};
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// DCH: 64-column chunks per head (1: d<=64, 2: d<=128, 3: d<=192); KS: QK^T k-steps = ceil(d/16);
+// DV: PV N extent (multiple of 16 >= d); KST/VST: K and V smem stages.
+template <int DCH, int KS, int DV, int KST, int VST>
+__global__ void __launch_bounds__(128)
+attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+            const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using namespace tc05;
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kChunk = 128 * 128;  // one [128 rows][64 bf16] swizzled chunk = 16 KB
+  constexpr uint32_t kTmemCols = (128 + DV <= 256) ? 256 : 512;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + DCH * kChunk;
+  const uint32_t sV = sK + KST * DCH * kChunk;
+  const uint32_t sP = sV + VST * DCH * kChunk;
+  const uint32_t bars = sP + 2 * kChunk;
+  const uint32_t q_full = bars, s_full = bars + 8, o_full = bars + 16;
+  auto k_full = [&](int s) { return bars + 24u + 8u * s; };
+  auto v_full = [&](int s) { return bars + 24u + 8u * (KST + s); };
+  const uint32_t tmem_slot = bars + 24u + 8u * (KST + VST);
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* genP = gen + (sP - base);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int col0 = head * p.dstride;
+  const int nkv = (p.Nk + 127) / 128;
+  const bool leader = threadIdx.x == 0;
+
+  if (leader) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(o_full, 1);
+    for (int s = 0; s < KST; ++s) mbar_init(k_full(s), 1);
+    for (int s = 0; s < VST; ++s) mbar_init(v_full(s), 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) { __syncwarp(); tmem_alloc(tmem_slot, kTmemCols); }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem, tO = tmem + 128;
+
+  auto load_k = [&](int j) {
+    const int st = j % KST;
+    mbar_expect_tx(k_full(st), DCH * kChunk);
+    for (int c = 0; c < DCH; ++c) tma_load_3d(sK + (st * DCH + c) * kChunk, &tmK, k_full(st), col0 + 64 * c, j * 128, b);
+  };
+  auto load_v = [&](int j) {
+    const int st = j % VST;
+    mbar_expect_tx(v_full(st), DCH * kChunk);
+    for (int c = 0; c < DCH; ++c) tma_load_3d(sV + (st * DCH + c) * kChunk, &tmV, v_full(st), col0 + 64 * c, j * 128, b);
+  };
+  auto keys_in_tile = [&](int j) {  // valid keys of tile j rounded up to the MMA granularity
+    int n = p.Nk - j * 128;
+    n = n > 128 ? 128 : n;
+    return (n + 15) & ~15;
+  };
+  auto issue_s = [&](int j) {
+    const int st = j % KST;
+    mbar_wait(k_full(st), (uint32_t)(j / KST) & 1u);
+    fence_after_sync();
+    const uint32_t idesc = make_idesc_bf16(128, keys_in_tile(j), 0, 0);
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+      const uint32_t off = (uint32_t)(k >> 2) * kChunk + (uint32_t)(k & 3) * 32u;
+      mma_f16_ss(tS, make_smem_desc_sw128(sQ + off, 16, 1024),
+                 make_smem_desc_sw128(sK + st * DCH * kChunk + off, 16, 1024), idesc, k != 0);
+    }
+    mma_commit(s_full);
+  };
+
+  if (leader) {
+    mbar_expect_tx(q_full, DCH * kChunk);
+    for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + c * kChunk, &tmQ, q_full, col0 + 64 * c, q0, b);
+    for (int j = 0; j < KST && j < nkv; ++j) load_k(j);
+    for (int j = 0; j < VST && j < nkv; ++j) load_v(j);
+    mbar_wait(q_full, 0);
+    issue_s(0);
+  }
+  __syncwarp();
+
+  const int row = warp * 32 + lane;
+  const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int j = 0; j < nkv; ++j) {
+    const int nk_valid = min(128, p.Nk - j * 128);
+    const int ncols = (nk_valid + 15) & ~15;
+    // ---- S_j ready ----
+    mbar_wait(s_full, (uint32_t)j & 1u);
+    fence_after_sync();
+    if (leader && j + KST < nkv) load_k(j + KST);  // K stage of tile j is free once S_j has completed
+    __syncwarp();
+    // pass 1: row max
+    float mx = -INFINITY;
+    for (int c = 0; c < ncols; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tS + lane_off + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (c + i < nk_valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+    }
+    const float m_new = fmaxf(m_run, mx * p.scale_log2);
+    const float alpha = ex2f(m_run - m_new);
+    // ---- PV_{j-1} done: O may be rescaled, P / V stage may be overwritten ----
+    if (j > 0) {
+      mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
+      fence_after_sync();
+      if (leader && j - 1 + VST < nkv) load_v(j - 1 + VST);
+      __syncwarp();
+      for (int c = 0; c < DV; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tO + lane_off + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        tmem_st16(tO + lane_off + c, v);
+      }
+      tmem_st_wait();
+    }
+    // pass 2: P = exp2(S*scale - m), row sum, bf16 P -> swizzled smem
+    float lsum = 0.f;
+    for (int c = 0; c < ncols; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tS + lane_off + c, v);
+      tmem_ld_wait();
+      float pf[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float e = ex2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_new));
+        pf[i] = (c + i < nk_valid) ? e : 0.f;
+        lsum += pf[i];
+      }
+      const int chunk = c >> 6;
+      const int u0 = (c & 63) >> 3;  // first 16-byte unit inside the 128-byte row
+      uint8_t* rowp = genP + chunk * kChunk + row * 128;
+      uint4 w0, w1;
+      w0.x = pack_bf16(pf[0], pf[1]);   w0.y = pack_bf16(pf[2], pf[3]);
+      w0.z = pack_bf16(pf[4], pf[5]);   w0.w = pack_bf16(pf[6], pf[7]);
+      w1.x = pack_bf16(pf[8], pf[9]);   w1.y = pack_bf16(pf[10], pf[11]);
+      w1.z = pack_bf16(pf[12], pf[13]); w1.w = pack_bf16(pf[14], pf[15]);
+      *reinterpret_cast<uint4*>(rowp + (((u0) ^ (row & 7)) << 4)) = w0;
+      *reinterpret_cast<uint4*>(rowp + (((u0 + 1) ^ (row & 7)) << 4)) = w1;
+    }
+    l_run = l_run * alpha + lsum;
+    m_run = m_new;
+    fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
+    fence_before_sync();
+    __syncthreads();
+    if (leader) {
+      fence_after_sync();
+      const int st = j % VST;
+      mbar_wait(v_full(st), (uint32_t)(j / VST) & 1u);
+      fence_after_sync();
+      const uint32_t idesc = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
+      const int ksteps = ncols >> 4;
+      for (int k = 0; k < ksteps; ++k) {
+        const uint64_t da = make_smem_desc_sw128(sP + (uint32_t)(k >> 2) * kChunk + (uint32_t)(k & 3) * 32u, 16, 1024);
+        const uint64_t db = make_smem_desc_sw128(sV + st * DCH * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
+        mma_f16_ss(tO, da, db, idesc, (j | k) != 0);
+      }
+      mma_commit(o_full);
+      if (j + 1 < nkv) issue_s(j + 1);  // S_{j+1} queues behind PV_j on the tensor pipe
+    }
+    __syncwarp();
+  }
+
+  // ---- epilogue: O / l -> bf16 ----
+  mbar_wait(o_full, (uint32_t)(nkv - 1) & 1u);
+  fence_after_sync();
+  const float inv_l = 1.f / l_run;
+  const int q = q0 + row;
+  const bool ok = q < p.Nq;
+  bf16* orow = p.out + ((long long)b * p.Nq + q) * p.ldo + head * p.d;
+  for (int c = 0; c < DV; c += 16) {
+    uint32_t v[16];
+    __syncwarp();
+    tmem_ld16(tO + lane_off + c, v);
+    tmem_ld_wait();
+    if (ok) {
+      uint4 w0, w1;
+      w0.x = pack_bf16(__uint_as_float(v[0]) * inv_l, __uint_as_float(v[1]) * inv_l);
+      w0.y = pack_bf16(__uint_as_float(v[2]) * inv_l, __uint_as_float(v[3]) * inv_l);
+      w0.z = pack_bf16(__uint_as_float(v[4]) * inv_l, __uint_as_float(v[5]) * inv_l);
+      w0.w = pack_bf16(__uint_as_float(v[6]) * inv_l, __uint_as_float(v[7]) * inv_l);
+      w1.x = pack_bf16(__uint_as_float(v[8]) * inv_l, __uint_as_float(v[9]) * inv_l);
+      w1.y = pack_bf16(__uint_as_float(v[10]) * inv_l, __uint_as_float(v[11]) * inv_l);
+      w1.z = pack_bf16(__uint_as_float(v[12]) * inv_l, __uint_as_float(v[13]) * inv_l);
+      w1.w = pack_bf16(__uint_as_float(v[14]) * inv_l, __uint_as_float(v[15]) * inv_l);
+      if (c + 8 <= p.d) *reinterpret_cast<uint4*>(orow + c) = w0;
+      if (c + 16 <= p.d) *reinterpret_cast<uint4*>(orow + c + 8) = w1;
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, kTmemCols);
+}
+
+template <int DCH, int KST, int VST>
+constexpr size_t attn_smem_bytes() {
+  return 1024 + (size_t)(DCH + KST * DCH + VST * DCH + 2) * 128 * 128 + 24 + 8 * (KST + VST) + 16;
+}
+
+// Q/K/V token matrices: [B][N][ld] bf16; head h of Q at q + h*dstride etc.
+struct AttnArgs {
+  const bf16 *q, *k, *v;
+  long long ldq, ldk, ldv;
+  int B, heads, Nq, Nk, d, dstride;
+  bf16* out;
+  long long ldo;
+};
+
+inline CUtensorMap make_tok_tmap(const bf16* base, int cols, int N, int B, long long ld) {
+  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)N, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)N * ld * 2};
+  uint32_t box[3] = {64, 128, 1};
+  uint32_t es[3] = {1, 1, 1};
+  return make_tmap_bf16(base, 3, dims, strides, box, es);
+}
+
+template <int DCH, int KS, int DV, int KST, int VST>
+inline void init_attn_t() {
+  SDTF_CUDA(cudaFuncSetAttribute(attn_kernel<DCH, KS, DV, KST, VST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)attn_smem_bytes<DCH, KST, VST>()));
+}
+// called once per process before any launch (and before any stream capture)
+inline void init_attn_kernels() {
+  init_attn_t<1, 3, 48, 2, 2>();
+  init_attn_t<2, 5, 80, 2, 2>();
+  init_attn_t<3, 10, 160, 1, 1>();
+}
+
+template <int DCH, int KS, int DV, int KST, int VST>
+inline void launch_attn_t(cudaStream_t stream, const AttnArgs& a, const AttnParams& p, const CUtensorMap& tq,
+                          const CUtensorMap& tk, const CUtensorMap& tv) {
+  auto kern = attn_kernel<DCH, KS, DV, KST, VST>;
+  constexpr size_t smem = attn_smem_bytes<DCH, KST, VST>();
+  dim3 grid((unsigned)ceil_div(a.Nq, 128), (unsigned)a.heads, (unsigned)a.B);
+  kern<<<grid, 128, smem, stream>>>(tq, tk, tv, p);
+  SDTF_CUDA(cudaGetLastError());
+}
+
+inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
+  AttnParams p;
+  p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.dstride = a.dstride;
+  p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)a.d));
+  p.out = a.out; p.ldo = a.ldo;
+  const int cols = a.heads * a.dstride;
+  CUtensorMap tq = make_tok_tmap(a.q, cols, a.Nq, a.B, a.ldq);
+  CUtensorMap tk = make_tok_tmap(a.k, cols, a.Nk, a.B, a.ldk);
+  CUtensorMap tv = make_tok_tmap(a.v, cols, a.Nk, a.B, a.ldv);
+  if (a.d == 40) {
+    SDTF_CHECK(a.dstride == 64, "d=40 heads must be stored zero-padded to 64 columns");
+    launch_attn_t<1, 3, 48, 2, 2>(stream, a, p, tq, tk, tv);
+  } else if (a.d == 80) {
+    SDTF_CHECK(a.dstride == 80, "d=80 heads are stored densely");
+    launch_attn_t<2, 5, 80, 2, 2>(stream, a, p, tq, tk, tv);
+  } else if (a.d == 160) {
+    SDTF_CHECK(a.dstride == 160, "d=160 heads are stored densely");
+    launch_attn_t<3, 10, 160, 1, 1>(stream, a, p, tq, tk, tv);
+  } else {
+    throw Error("attention: unsupported head size " + std::to_string(a.d));
+  }
+}
+
+}  // namespace sdtf

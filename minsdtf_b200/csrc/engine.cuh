@@ -1,0 +1,276 @@
+// engine.cuh — engine state: device arena, weight store + packing, and the launch context every model graph
+// issues its kernels through (dry-run aware, so the workspace high-water mark is measured before anything runs).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "attn.cuh"
+#include "gemm_host.cuh"
+#include "ops.cuh"
+
+namespace sdtf {
+
+// ----------------------------------------------------------------------------------------------------------
+// Bump arena over one cudaMalloc block.  Stream order makes reuse after release() safe: every kernel of a
+// forward pass is enqueued on the engine's single stream.
+// ----------------------------------------------------------------------------------------------------------
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;  // dry: only measure
+  void* alloc(size_t bytes) {
+    size_t a = (off + 1023) & ~(size_t)1023;
+    size_t end = a + ((bytes + 1023) & ~(size_t)1023);
+    if (!dry && end > cap) throw Error("workspace arena exhausted (internal sizing error)");
+    off = end;
+    if (off > peak) peak = off;
+    // dry runs hand out a dummy non-null, suitably aligned address that is never dereferenced
+    return dry ? reinterpret_cast<void*>((uintptr_t)0x10000000 + a) : base + a;
+  }
+  template <class T>
+  T* alloc_n(size_t n) { return reinterpret_cast<T*>(alloc(n * sizeof(T))); }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+// persistent device allocations (weights), freed with the engine
+struct DevicePool {
+  std::vector<void*> ptrs;
+  size_t bytes = 0;
+  void* alloc(size_t n) {
+    void* p = nullptr;
+    SDTF_CUDA(cudaMalloc(&p, n ? n : 16));
+    ptrs.push_back(p);
+    bytes += n;
+    return p;
+  }
+  ~DevicePool() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+};
+
+struct RawTensor {  // a checkpoint tensor staged on the device as fp32, PyTorch layout
+  float* p = nullptr;
+  std::vector<int64_t> shape;
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto s : shape) n *= s;
+    return n;
+  }
+};
+
+struct NormW {
+  float* gamma = nullptr;
+  float* beta = nullptr;
+  int C = 0;
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// Launch context
+// ----------------------------------------------------------------------------------------------------------
+struct Ctx {
+  cudaStream_t st = nullptr;
+  Arena* ws = nullptr;
+  bool dry = false;
+  int launches = 0;
+  double* gn_stats = nullptr;  // B*64 doubles scratch
+
+  View alloc_view(int B, int H, int W, int C) {
+    View v;
+    v.p = ws->alloc_n<bf16>((size_t)B * H * W * C);
+    v.B = B; v.H = H; v.W = W; v.C = C; v.ld = C;
+    return v;
+  }
+
+  void conv(const ConvArgs& a) {
+    ++launches;
+    if (!dry) launch_conv(st, a);
+  }
+  // y = conv(x) (+bias) (+temb) (+res) ; out view may be a channel slice
+  void conv(const View& x, const PackedWeight& w, const View& out, int stride = 1, int pad = -1, const View* res = nullptr,
+            const float* temb = nullptr, int temb_ld = 0, int act = ACT_NONE, const View* x2 = nullptr) {
+    ConvArgs a;
+    a.a0 = x;
+    if (x2) a.a1 = *x2;
+    a.w = &w;
+    a.stride = stride;
+    const int p = pad >= 0 ? pad : (w.kh == 3 ? 1 : 0);
+    a.pad_t = a.pad_l = p;
+    a.outH = out.H; a.outW = out.W;
+    a.temb = temb; a.temb_ld = temb_ld;
+    if (res) { a.res = res->p; a.res_ld = res->ld; }
+    a.out = out.p; a.out_ld = out.ld;
+    a.act = act;
+    conv(a);
+  }
+  void groupnorm(const View& x, const NormW& n, bool silu, const View& y) {
+    launches += 2;
+    if (!dry) launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn_stats);
+  }
+  void layernorm(const View& x, const NormW& n, const View& y) {
+    ++launches;
+    if (!dry) launch_layernorm(st, x.p, x.ld, x.C, x.pixels(), n.gamma, n.beta, y.p, y.ld);
+  }
+  void attention(const AttnArgs& a) {
+    ++launches;
+    if (!dry) launch_attn(st, a);
+  }
+  void upsample2x(const View& x, const View& y) {
+    ++launches;
+    if (!dry) launch_upsample2x(st, x, y.p);
+  }
+  void add_inplace(const View& y, const bf16* c) {
+    ++launches;
+    if (dry) return;
+    long long total = y.pixels() * (y.C / 8);
+    long long blocks = ceil_div_ll(total, 256 * 4);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    add_inplace_kernel<<<(unsigned)blocks, 256, 0, st>>>(y.p, y.ld, y.C, y.pixels(), c);
+    SDTF_CUDA(cudaGetLastError());
+  }
+  void skinny(const float* x, int M, int K, const bf16* W, const float* bias, int N, bool silu, float* out, int ldo) {
+    ++launches;
+    if (!dry) launch_skinny_linear(st, x, M, K, W, bias, N, silu, out, ldo);
+  }
+  void cast_pad(const float* x, long long pixels, int Cs, int Cd, float scale, bf16* y, bool dup) {
+    ++launches;
+    if (!dry) launch_cast_pad(st, x, pixels, Cs, Cd, scale, y, dup);
+  }
+  void cast_out(const bf16* x, long long ld, long long pixels, int Cs, float* y) {
+    ++launches;
+    if (!dry) launch_cast_out(st, x, ld, pixels, Cs, y);
+  }
+  void memset0(void* p, size_t bytes) {
+    if (!dry) SDTF_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+  }
+};
+
+// ----------------------------------------------------------------------------------------------------------
+// Weight store: staged raw tensors by checkpoint key, and helpers that pack them for the kernels
+// ----------------------------------------------------------------------------------------------------------
+struct WeightStore {
+  std::unordered_map<std::string, RawTensor> raw;
+  DevicePool pool;
+  cudaStream_t st = nullptr;
+  std::vector<std::string> missing;
+
+  const RawTensor* find(const std::string& key) {
+    auto it = raw.find(key);
+    if (it == raw.end()) {
+      missing.push_back(key);
+      return nullptr;
+    }
+    return &it->second;
+  }
+  int* upload_map(const std::vector<int>& m) {
+    int* d = nullptr;
+    SDTF_CUDA(cudaMallocAsync(&d, m.size() * sizeof(int), st));
+    SDTF_CUDA(cudaMemcpyAsync(d, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    SDTF_CUDA(cudaStreamSynchronize(st));  // the host vector may die right after this call
+    return d;
+  }
+  void free_map(int* d) { SDTF_CUDA(cudaFreeAsync(d, st)); }
+
+  // pack rows of `key` ([O][I][kh][kw] or [O][I]) into dst [taps][Ntot][Kp] at row n0, column k0
+  void pack_into(bf16* dst, int Ntot, int Kp, int n0, int k0, const RawTensor& t, const std::vector<int>* row_map, float scale) {
+    const int O = (int)t.shape[0], I = (int)t.shape[1];
+    const int taps = t.shape.size() == 4 ? (int)(t.shape[2] * t.shape[3]) : 1;
+    const int nrows = row_map ? (int)row_map->size() : O;
+    int* dm = row_map ? upload_map(*row_map) : nullptr;
+    const long long total = (long long)taps * nrows * I;
+    long long blocks = ceil_div_ll(total, 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    if (blocks < 1) blocks = 1;
+    pack_weight_kernel<<<(unsigned)blocks, 256, 0, st>>>(t.p, I, taps, dm, nrows, n0, Ntot, Kp, k0, scale, dst);
+    SDTF_CUDA(cudaGetLastError());
+    if (dm) free_map(dm);
+  }
+  float* pack_vec(const RawTensor& t, const std::vector<int>* row_map, float scale, float* dst = nullptr, int n0 = 0) {
+    const int n = row_map ? (int)row_map->size() : (int)t.numel();
+    if (!dst) dst = (float*)pool.alloc((size_t)n * 4);
+    int* dm = row_map ? upload_map(*row_map) : nullptr;
+    gather_f32_kernel<<<ceil_div(n, 256), 256, 0, st>>>(t.p, dm, n, scale, dst + n0);
+    SDTF_CUDA(cudaGetLastError());
+    if (dm) free_map(dm);
+    return dst;
+  }
+
+  // plain conv / linear: key.weight [+ key.bias]
+  PackedWeight conv(const std::string& key, bool bias = true, float scale = 1.f, const std::vector<int>* row_map = nullptr) {
+    PackedWeight pw;
+    const RawTensor* w = find(key + ".weight");
+    const RawTensor* b = bias ? find(key + ".bias") : nullptr;
+    if (!w || (bias && !b)) return pw;
+    const int I = (int)w->shape[1];
+    pw.kh = w->shape.size() == 4 ? (int)w->shape[2] : 1;
+    pw.kw = w->shape.size() == 4 ? (int)w->shape[3] : 1;
+    pw.N = row_map ? (int)row_map->size() : (int)w->shape[0];
+    pw.K = (I + 7) / 8 * 8;
+    const size_t n = (size_t)pw.kh * pw.kw * pw.N * pw.K;
+    pw.w = (bf16*)pool.alloc(n * 2);
+    SDTF_CUDA(cudaMemsetAsync(pw.w, 0, n * 2, st));
+    pack_into(pw.w, pw.N, pw.K, 0, 0, *w, row_map, scale);
+    if (b) pw.bias = pack_vec(*b, row_map, scale);
+    return pw;
+  }
+  NormW norm(const std::string& key) {
+    NormW n;
+    const RawTensor* g = find(key + ".weight");
+    const RawTensor* b = find(key + ".bias");
+    if (!g || !b) return n;
+    n.C = (int)g->numel();
+    n.gamma = pack_vec(*g, nullptr, 1.f);
+    n.beta = pack_vec(*b, nullptr, 1.f);
+    return n;
+  }
+  // several [O_i][I] matrices stacked along N (q|k|v, k|v); heads optionally zero-padded from d to dpad rows
+  PackedWeight stack(const std::vector<std::string>& keys, int heads, int d, int dpad) {
+    PackedWeight pw;
+    std::vector<const RawTensor*> ts;
+    for (auto& k : keys) ts.push_back(find(k + ".weight"));
+    for (auto t : ts)
+      if (!t) return pw;
+    const int I = (int)ts[0]->shape[1];
+    std::vector<int> map;
+    for (int h = 0; h < heads; ++h)
+      for (int j = 0; j < dpad; ++j) map.push_back(j < d ? h * d + j : -1);
+    const int per = heads * dpad;
+    pw.N = per * (int)ts.size();
+    pw.K = (I + 7) / 8 * 8;
+    pw.w = (bf16*)pool.alloc((size_t)pw.N * pw.K * 2);
+    SDTF_CUDA(cudaMemsetAsync(pw.w, 0, (size_t)pw.N * pw.K * 2, st));
+    for (size_t i = 0; i < ts.size(); ++i) pack_into(pw.w, pw.N, pw.K, (int)i * per, 0, *ts[i], &map, 1.f);
+    return pw;
+  }
+  // GEGLU projection [8C][C]: rows interleaved per 160-wide N tile as [80 value | 80 gate]
+  PackedWeight geglu(const std::string& key) {
+    const RawTensor* w = find(key + ".weight");
+    PackedWeight pw;
+    if (!w) return pw;
+    const int N = (int)w->shape[0], half = N / 2;
+    std::vector<int> map(N);
+    for (int t = 0; t < N / 160; ++t)
+      for (int j = 0; j < 80; ++j) {
+        map[t * 160 + j] = t * 80 + j;
+        map[t * 160 + 80 + j] = half + t * 80 + j;
+      }
+    pw = conv(key, true, 1.f, &map);
+    pw.geglu_half = 80;
+    return pw;
+  }
+  void drop_raw(const std::string& prefix) {
+    for (auto it = raw.begin(); it != raw.end();) {
+      if (it->first.compare(0, prefix.size(), prefix) == 0) {
+        cudaFree(it->second.p);
+        it = raw.erase(it);
+      } else {
+        ++it;
+      }
+    }
+  }
+};
+
+}  // namespace sdtf

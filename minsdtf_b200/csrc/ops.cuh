@@ -1,0 +1,502 @@
+// ops.cuh — the HBM-bound kernels of the path: GroupNorm(+SiLU), LayerNorm, nearest upsample, row softmax,
+// the tiny time-embedding linears, the fused CFG + scheduler step, weight packing and dtype conversions.
+// All use 128-bit loads/stores on NHWC bf16 and warp-shuffle reductions.
+#pragma once
+#include "common.cuh"
+
+namespace sdtf {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __bfloat162float(h[i].x);
+    f[2 * i + 1] = __bfloat162float(h[i].y);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 h;
+  h = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t*>(&h);
+  h = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t*>(&h);
+  return u;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// GroupNorm(32 groups, eps 1e-5, biased variance) [+ SiLU]   (reference: keras GroupNormalization at
+// diffusion_model.py:27-28,32-33,57,277-278; layers.py:32,66-79; image_decoder.py:51-52)
+// Phase 1: per-(sample, group) sum / sum-of-squares.  Each thread owns one 8-channel vector position and
+// strides over pixels, so its loads are 16-byte and warp-contiguous; per-channel partials are folded into
+// 32 smem group bins, then one fp64 atomic per bin per CTA.
+// Phase 2: normalise + affine (+ SiLU) -> bf16.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+gn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, int pix_per_cta, double* __restrict__ stats) {
+  const int vecs = C >> 3;
+  const int lanes = blockDim.x / vecs;  // pixels processed in parallel by this CTA
+  const int cv = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+  const int b = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  const long long p1 = min(HW, p0 + pix_per_cta);
+  __shared__ float bins[64];
+  if (threadIdx.x < 64) bins[threadIdx.x] = 0.f;
+  __syncthreads();
+  float s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+  if (pl < lanes) {
+    const bf16* base = x + ((long long)b * HW) * ld + cv * 8;
+    for (long long p = p0 + pl; p < p1; p += lanes) {
+      const uint4 u = *reinterpret_cast<const uint4*>(base + p * ld);
+      float f[8];
+      unpack8(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] += f[i] * f[i];
+      }
+    }
+    const int gs = C >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = (cv * 8 + i) / gs;
+      atomicAdd(&bins[2 * g], s[i]);
+      atomicAdd(&bins[2 * g + 1], q[i]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) atomicAdd(&stats[(long long)b * 64 + threadIdx.x], (double)bins[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, const double* __restrict__ stats,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, bf16* __restrict__ y,
+                long long ldy) {
+  const int b = blockIdx.y;
+  __shared__ float mean[32], rstd[32];
+  if (threadIdx.x < 32) {
+    const double n = (double)HW * (C >> 5);
+    const double m = stats[(long long)b * 64 + 2 * threadIdx.x] / n;
+    double var = stats[(long long)b * 64 + 2 * threadIdx.x + 1] / n - m * m;
+    if (var < 0) var = 0;
+    mean[threadIdx.x] = (float)m;
+    rstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+  __syncthreads();
+  const int vecs = C >> 3, gs = C >> 5;
+  const long long total = HW * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / vecs;
+    const int cv = (int)(i - p * vecs);
+    const uint4 u = *reinterpret_cast<const uint4*>(x + ((long long)b * HW + p) * ld + cv * 8);
+    float f[8];
+    unpack8(u, f);
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + 4));
+    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int g = (cv * 8 + k) / gs;
+      float v = (f[k] - mean[g]) * rstd[g] * ga[k] + be[k];
+      if (silu) v = v / (1.f + __expf(-v));
+      f[k] = v;
+    }
+    *reinterpret_cast<uint4*>(y + ((long long)b * HW + p) * ldy + cv * 8) = pack8(f);
+  }
+}
+
+// x: NHWC view (possibly a slice of a wider buffer); y dense [B][HW][C] (ldy may differ); stats: B*64 doubles
+inline void launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, const float* beta, bool silu, bf16* y,
+                             long long ldy, double* stats) {
+  SDTF_CHECK(x.C % 32 == 0 && x.C % 8 == 0, "GroupNorm needs C % 32 == 0");
+  const long long HW = (long long)x.H * x.W;
+  SDTF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * x.B, st));
+  const int vecs = x.C / 8;
+  int threads = (512 / vecs) * vecs;
+  if (threads == 0) threads = vecs;  // C > 4096 never happens here
+  SDTF_CHECK(threads <= 512, "GroupNorm: too many channels");
+  // enough CTAs to fill 148 SMs a few times over
+  long long want = (148 * 4 + x.B - 1) / x.B;
+  long long ppc = ceil_div_ll(HW, want);
+  const int lanes = threads / vecs;
+  if (ppc < lanes * 4) ppc = lanes * 4;
+  dim3 g1((unsigned)ceil_div_ll(HW, ppc), (unsigned)x.B);
+  gn_stats_kernel<<<g1, threads, 0, st>>>(x.p, x.ld, x.C, HW, (int)ppc, stats);
+  SDTF_CUDA(cudaGetLastError());
+  const long long total = HW * vecs;
+  long long blocks = ceil_div_ll(total, 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  dim3 g2((unsigned)blocks, (unsigned)x.B);
+  gn_apply_kernel<<<g2, 256, 0, st>>>(x.p, x.ld, x.C, HW, stats, gamma, beta, silu ? 1 : 0, y, ldy);
+  SDTF_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------
+// LayerNorm(eps 1e-5) over C, one warp per token (reference: diffusion_model.py:84,86,88)
+// ------------------------------------------------------------------------------------------------------
+template <int MAXV>  // max 8-channel vectors per lane
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const bf16* __restrict__ x, long long ld, int C, long long rows, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, bf16* __restrict__ y, long long ldy) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const int vecs = C >> 3;
+  float f[MAXV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int cv = lane + 32 * j;
+    if (cv < vecs) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + row * ld + cv * 8);
+      unpack8(u, f[j]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += f[j][k];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int cv = lane + 32 * j;
+    if (cv < vecs) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = f[j][k] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    const int cv = lane + 32 * j;
+    if (cv < vecs) {
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        o[k] = (f[j][k] - mean) * rstd * __ldg(gamma + cv * 8 + k) + __ldg(beta + cv * 8 + k);
+      *reinterpret_cast<uint4*>(y + row * ldy + cv * 8) = pack8(o);
+    }
+  }
+}
+
+inline void launch_layernorm(cudaStream_t st, const bf16* x, long long ld, int C, long long rows, const float* gamma,
+                             const float* beta, bf16* y, long long ldy) {
+  SDTF_CHECK(C % 8 == 0 && C <= 32 * 8 * 5, "LayerNorm: C must be a multiple of 8 and <= 1280");
+  const unsigned blocks = (unsigned)ceil_div_ll(rows, 8);
+  const int vecs = C / 8;
+  if (vecs <= 64) layernorm_kernel<2><<<blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+  else if (vecs <= 96) layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+  else layernorm_kernel<5><<<blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+  SDTF_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------
+// nearest 2x upsample (UpSampling2D(2): diffusion_model.py:135, image_decoder.py:36,41,46)
+// ------------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const bf16* __restrict__ x, long long ld, int B, int H, int W, int C, bf16* __restrict__ y) {
+  const int vecs = C >> 3;
+  const long long total = (long long)B * (2 * H) * (2 * W) * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % vecs);
+    long long p = i / vecs;
+    const int ox = (int)(p % (2 * W)); p /= (2 * W);
+    const int oy = (int)(p % (2 * H));
+    const int b = (int)(p / (2 * H));
+    const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * ld + cv * 8);
+    *reinterpret_cast<uint4*>(y + i * 8) = u;
+  }
+}
+inline void launch_upsample2x(cudaStream_t st, const View& x, bf16* y) {
+  const long long total = (long long)x.B * 4 * x.H * x.W * (x.C / 8);
+  long long blocks = ceil_div_ll(total, 256 * 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  upsample2x_kernel<<<(unsigned)blocks, 256, 0, st>>>(x.p, x.ld, x.B, x.H, x.W, x.C, y);
+  SDTF_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------
+// row softmax fp32 -> bf16 (VAE mid-block attention, layers.py:48-50), one CTA per row
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, long long lds, int n, bf16* __restrict__ p, long long ldp) {
+  const long long row = blockIdx.x;
+  const float* sr = s + row * lds;
+  __shared__ float red[8];
+  float mx = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, sr[i]);
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += __expf(sr[i] - mx);
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  bf16* pr = p + row * ldp;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) pr[i] = __float2bfloat16(__expf(sr[i] - mx) * inv);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// skinny linear for the time-embedding chain (diffusion_model.py:184-188 and every ResBlock's
+// time_emb_proj :30,47): out[m][n] = act(sum_k x[m][k] * W[n][k] + b[n]), M <= 64 rows, one warp per n.
+// ------------------------------------------------------------------------------------------------------
+template <int MT>
+__global__ void __launch_bounds__(256)
+skinny_linear_kernel(const float* __restrict__ x, int M, int K, const bf16* __restrict__ W, const float* __restrict__ bias,
+                     int N, int silu, float* __restrict__ out, int ldo) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int lane = threadIdx.x & 31;
+  for (int m0 = 0; m0 < M; m0 += MT) {
+    float acc[MT];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) acc[m] = 0.f;
+    for (int k = lane * 8; k < K; k += 256) {
+      const uint4 u = *reinterpret_cast<const uint4*>(W + (long long)n * K + k);
+      float w[8];
+      unpack8(u, w);
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        if (m0 + m < M) {
+          const float4 a0 = *reinterpret_cast<const float4*>(x + (long long)(m0 + m) * K + k);
+          const float4 a1 = *reinterpret_cast<const float4*>(x + (long long)(m0 + m) * K + k + 4);
+          acc[m] += a0.x * w[0] + a0.y * w[1] + a0.z * w[2] + a0.w * w[3] + a1.x * w[4] + a1.y * w[5] + a1.z * w[6] + a1.w * w[7];
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      float v = warp_sum(acc[m]);
+      if (lane == 0 && m0 + m < M) {
+        v += bias ? bias[n] : 0.f;
+        if (silu) v = v / (1.f + __expf(-v));
+        out[(long long)(m0 + m) * ldo + n] = v;
+      }
+    }
+  }
+}
+inline void launch_skinny_linear(cudaStream_t st, const float* x, int M, int K, const bf16* W, const float* bias, int N,
+                                 bool silu, float* out, int ldo) {
+  SDTF_CHECK(K % 8 == 0, "skinny linear: K % 8");
+  skinny_linear_kernel<8><<<(unsigned)ceil_div(N, 8), 256, 0, st>>>(x, M, K, W, bias, N, silu ? 1 : 0, out, ldo);
+  SDTF_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Fused CFG combine + CFG-rescale + scheduler update (+ inpaint blend)  — one CTA per sample.
+//   reference: stable_diffusion.py:458 (combine), :304-315 (rescale_noise_cfg, population std over h,w,c),
+//   scheduler.py:285-312 (DDIM / TCD update, coefficients pre-combined on the host in fp64),
+//   stable_diffusion.py:469-475 (inpaint: latent = noised_init(t)*(1-m) + latent*m).
+// latent' = ca * latent + cb * eps (+ cn * noise);  writes the fp32 master latent and the bf16 8-channel
+// copies (duplicated for the uncond / cond halves of the next UNet batch).
+// ------------------------------------------------------------------------------------------------------
+struct StepCoef {
+  float guidance, rescale;  // guidance <= 0: eps = eps_c (no CFG)
+  float ca, cb, cn;         // latent' = ca*latent + cb*eps + cn*noise
+  float sig_t, noi_t;       // inpaint re-noising of the init latent at the current t
+};
+
+__global__ void __launch_bounds__(512)
+cfg_sched_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c, const float* __restrict__ latent,
+                 const StepCoef* __restrict__ coefs, const int* __restrict__ step_ptr, const float* __restrict__ noise,
+                 const float* __restrict__ mask,
+                 const float* __restrict__ init_latent, const float* __restrict__ init_noise, int n_per_sample,
+                 float* __restrict__ out, bf16* __restrict__ out_bf16 /* [2B or B][HW][8] */, int B, int dup) {
+  const int step = step_ptr ? *step_ptr : 0;
+  const StepCoef c = coefs[step];
+  const int b = blockIdx.x;
+  if (noise) noise += (long long)step * B * n_per_sample;  // per-step TCD noise table
+  const long long off = (long long)b * n_per_sample;
+  __shared__ float red[2][16];
+  __shared__ float stat[4];
+  const bool cfg = c.guidance > 0.f && eps_u != nullptr;
+  float factor = 1.f;
+  if (cfg && c.rescale > 0.f) {
+    // population std of eps_c and of the combined eps over the whole sample (two-pass, fp32)
+    float s1 = 0.f, s2 = 0.f;
+    for (int i = threadIdx.x; i < n_per_sample; i += blockDim.x) {
+      const float u = eps_u[off + i], t = eps_c[off + i];
+      s1 += t;
+      s2 += u + c.guidance * (t - u);
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, d = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; d += red[1][i]; }
+      stat[0] = a / n_per_sample; stat[1] = d / n_per_sample;
+    }
+    __syncthreads();
+    const float m1 = stat[0], m2 = stat[1];
+    float q1 = 0.f, q2 = 0.f;
+    for (int i = threadIdx.x; i < n_per_sample; i += blockDim.x) {
+      const float u = eps_u[off + i], t = eps_c[off + i];
+      const float e = u + c.guidance * (t - u);
+      q1 += (t - m1) * (t - m1);
+      q2 += (e - m2) * (e - m2);
+    }
+    q1 = warp_sum(q1); q2 = warp_sum(q2);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = q1; red[1][threadIdx.x >> 5] = q2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float a = 0.f, d = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { a += red[0][i]; d += red[1][i]; }
+      const float std_text = sqrtf(a / n_per_sample), std_cfg = sqrtf(d / n_per_sample) + 1e-5f;
+      stat[2] = c.rescale * (std_text / std_cfg) + (1.f - c.rescale);
+    }
+    __syncthreads();
+    factor = stat[2];
+  }
+  for (int i = threadIdx.x; i < n_per_sample; i += blockDim.x) {
+    const float t = eps_c[off + i];
+    float e = t;
+    if (cfg) {
+      const float u = eps_u[off + i];
+      e = (u + c.guidance * (t - u)) * factor;
+    }
+    float x = c.ca * latent[off + i] + c.cb * e;
+    if (noise) x += c.cn * noise[off + i];
+    if (mask) {
+      const float mk = mask[i >> 2];  // mask is (h, w, 1), shared by all samples and channels
+      const float orig = c.sig_t * init_latent[i] + c.noi_t * init_noise[off + i];
+      x = orig * (1.f - mk) + x * mk;
+    }
+    out[off + i] = x;
+    if (out_bf16) {
+      const int pix = i >> 2, ch = i & 3;
+      const long long hw = n_per_sample >> 2;
+      out_bf16[((long long)b * hw + pix) * 8 + ch] = __float2bfloat16(x);
+      if (dup) out_bf16[((long long)(b + B) * hw + pix) * 8 + ch] = __float2bfloat16(x);
+    }
+  }
+}
+
+__global__ void step_advance_kernel(int* step) { *step += 1; }
+// t_emb table row select: out[b][:] = table[*step][:] for all b
+__global__ void temb_select_kernel(const float* __restrict__ table, const int* __restrict__ step_ptr, int dim, int B,
+                                   float* __restrict__ out) {
+  const int step = *step_ptr;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * dim; i += gridDim.x * blockDim.x)
+    out[i] = table[(long long)step * dim + (i % dim)];
+}
+// y(view) += c(dense bf16)   (ControlNet residual injection, diffusion_model.py:230-234)
+__global__ void add_inplace_kernel(bf16* __restrict__ y, long long ld, int C, long long pixels, const bf16* __restrict__ c) {
+  const int vecs = C >> 3;
+  const long long total = pixels * vecs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / vecs;
+    const int cv = (int)(i - p * vecs);
+    uint4* yp = reinterpret_cast<uint4*>(y + p * ld + cv * 8);
+    float a[8], b[8];
+    unpack8(*yp, a);
+    unpack8(*reinterpret_cast<const uint4*>(c + i * 8), b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += b[k];
+    *yp = pack8(a);
+  }
+}
+
+// fp32 [B][HW][Cs] -> bf16 [B*(dup?2:1)][HW][Cd] (Cd >= Cs, zero padded), scaled
+__global__ void cast_pad_kernel(const float* __restrict__ x, long long pixels, int Cs, int Cd, float scale, bf16* __restrict__ y,
+                                int dup) {
+  const long long total = pixels * Cd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / Cd;
+    const int c = (int)(i - p * Cd);
+    const bf16 v = __float2bfloat16(c < Cs ? x[p * Cs + c] * scale : 0.f);
+    y[i] = v;
+    if (dup) y[total + i] = v;
+  }
+}
+inline void launch_cast_pad(cudaStream_t st, const float* x, long long pixels, int Cs, int Cd, float scale, bf16* y, bool dup) {
+  long long blocks = ceil_div_ll(pixels * Cd, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_pad_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, pixels, Cs, Cd, scale, y, dup ? 1 : 0);
+  SDTF_CUDA(cudaGetLastError());
+}
+
+// bf16 NHWC (ld) first Cs channels -> fp32 dense
+__global__ void cast_out_kernel(const bf16* __restrict__ x, long long ld, long long pixels, int Cs, float* __restrict__ y) {
+  const long long total = pixels * Cs;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / Cs;
+    y[i] = __bfloat162float(x[p * ld + (i - p * Cs)]);
+  }
+}
+inline void launch_cast_out(cudaStream_t st, const bf16* x, long long ld, long long pixels, int Cs, float* y) {
+  long long blocks = ceil_div_ll(pixels * Cs, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cast_out_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ld, pixels, Cs, y);
+  SDTF_CUDA(cudaGetLastError());
+}
+
+// decoded fp32 [pixels][3] in ~[-1,1] -> uint8 with the reference's arithmetic:
+// clip(((d + 1) * 0.5 [blend with source]) * 255, 0, 255) truncated (stable_diffusion.py:483-486)
+__global__ void to_uint8_kernel(const float* __restrict__ d, long long n, const float* __restrict__ src_img,
+                                const float* __restrict__ src_mask, long long n_per_sample, uint8_t* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = (d[i] + 1.f) * 0.5f;
+    if (src_img) {
+      const long long j = i % n_per_sample;
+      const float m = src_mask[j / 3];
+      v = src_img[j] * (1.f - m) + v * m;
+    }
+    v = fminf(fmaxf(v * 255.f, 0.f), 255.f);
+    out[i] = (uint8_t)v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// weight packing: PyTorch layout fp32 [O][I][taps] -> bf16 [taps][Ntot][Kp] rows n0 + [0, nrows)
+//   row_map[r] = source output channel for packed row n0 + r (or -1 for a zero row); scale folds constants.
+// ------------------------------------------------------------------------------------------------------
+__global__ void pack_weight_kernel(const float* __restrict__ src, int I, int taps, const int* __restrict__ row_map, int nrows,
+                                   int n0, int Ntot, int Kp, int k0, float scale, bf16* __restrict__ dst) {
+  const long long total = (long long)taps * nrows * I;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % I);
+    long long r = i / I;
+    const int row = (int)(r % nrows);
+    const int t = (int)(r / nrows);
+    const int so = row_map ? row_map[row] : row;
+    const float v = so >= 0 ? src[((long long)so * I + k) * taps + t] * scale : 0.f;
+    dst[((long long)t * Ntot + n0 + row) * Kp + k0 + k] = __float2bfloat16(v);
+  }
+}
+
+__global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ row_map, int n, float scale,
+                                  float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int so = row_map ? row_map[i] : i;
+    dst[i] = so >= 0 ? src[so] * scale : 0.f;
+  }
+}
+
+}  // namespace sdtf

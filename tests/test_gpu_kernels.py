@@ -1,0 +1,90 @@
+"""GPU unit tests of the individual kernels, each against a plain torch fp32 reference of the same op (fed the same
+bf16-rounded inputs, so the tolerance only has to cover fp32-accumulate + one bf16 output rounding)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from minsdtf_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bf(x):
+    return torch.as_tensor(x).to(torch.bfloat16).to(torch.float32)
+
+
+def test_conv_gemm_standalone_cases():
+    """tests/cuda/test_gemm.cu: 18 conv / linear / GEGLU / concat / stride-2 cases vs a naive CUDA reference."""
+    from minsdtf_b200 import build
+    exe = build.build_test_gemm()
+    r = subprocess.run(["timeout", "300", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "ALL CASES PASSED" in r.stdout
+
+
+@pytest.mark.parametrize("B,Nq,Nk,heads,d", [
+    (2, 256, 256, 8, 40),      # one q tile per 128, 2 kv tiles
+    (1, 4096, 4096, 8, 40),    # 64x64 latent self-attention
+    (2, 1024, 1024, 8, 80),
+    (2, 256, 256, 8, 160),
+    (2, 64, 64, 8, 160),       # 8x8 mid block: fewer queries than a tile
+    (2, 1024, 77, 8, 40),      # cross-attention, ragged keys
+    (2, 256, 77, 8, 160),
+    (1, 1024, 154, 8, 80),     # long-prompt context (2 x 77)
+    (1, 300, 200, 8, 40),      # ragged queries and keys
+])
+def test_attention_matches_torch(engine, B, Nq, Nk, heads, d):
+    g = torch.Generator().manual_seed(B * 1000 + Nq + Nk + d)
+    C = heads * d
+    q = _bf(torch.randn(B, Nq, C, generator=g))
+    k = _bf(torch.randn(B, Nk, C, generator=g))
+    v = _bf(torch.randn(B, Nk, C, generator=g))
+    out = np.empty((B, Nq, C), np.float32)
+    dl = _lib.DL()
+    engine._check(engine._lib.sdtf_test_attention(engine._h, dl(q.numpy()), dl(k.numpy()), dl(v.numpy()), heads, dl(out)))
+    qh = q.view(B, Nq, heads, d).permute(0, 2, 1, 3).cuda()
+    kh = k.view(B, Nk, heads, d).permute(0, 2, 1, 3).cuda()
+    vh = v.view(B, Nk, heads, d).permute(0, 2, 1, 3).cuda()
+    s = torch.matmul(qh, kh.transpose(-1, -2)) * d ** -0.5
+    ref = torch.matmul(torch.softmax(s, -1), vh).permute(0, 2, 1, 3).reshape(B, Nq, C).cpu().numpy()
+    err = np.abs(out - ref).max()
+    assert np.isfinite(out).all()
+    assert err < 2e-2, f"max abs err {err} (ref max {np.abs(ref).max()})"
+
+
+@pytest.mark.parametrize("B,H,W,C,mode", [
+    (2, 64, 64, 320, 1), (2, 32, 32, 640, 0), (2, 16, 16, 1280, 1), (2, 8, 8, 2560, 1), (1, 32, 32, 960, 1),
+    (1, 16, 16, 1920, 1), (1, 128, 128, 128, 1), (1, 64, 64, 512, 0), (3, 24, 24, 256, 1),
+    (2, 64, 64, 320, 2), (2, 32, 32, 640, 2), (2, 16, 16, 1280, 2),
+])
+def test_norms_match_torch(engine, B, H, W, C, mode):
+    g = torch.Generator().manual_seed(C + mode)
+    x = _bf(torch.randn(B, H, W, C, generator=g) * 1.5 + 0.3)
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.05 * torch.randn(C, generator=g)
+    out = np.empty((B, H, W, C), np.float32)
+    dl = _lib.DL()
+    engine._check(engine._lib.sdtf_test_norm(engine._h, dl(x.numpy()), dl(gamma.numpy()), dl(beta.numpy()), mode, dl(out)))
+    if mode == 2:
+        ref = torch.nn.functional.layer_norm(x, (C,), gamma, beta, eps=1e-5)
+    else:
+        ref = torch.nn.functional.group_norm(x.permute(0, 3, 1, 2), 32, gamma, beta, eps=1e-5)
+        if mode == 1:
+            ref = torch.nn.functional.silu(ref)
+        ref = ref.permute(0, 2, 3, 1)
+    err = (torch.as_tensor(out) - ref).abs().max().item()
+    assert err < 3e-2, err
+
+
+def test_engine_rejects_bad_arguments(engine):
+    """error behaviour at the boundary: bad shapes come back as error codes with a message, not crashes"""
+    from minsdtf_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        engine.unet(np.zeros((1, 16, 16, 3), np.float32), np.zeros((1, 320), np.float32), np.zeros((1, 77, 768), np.float32))
+    with pytest.raises(EngineError):
+        engine._check(engine._lib.sdtf_finalize_weights(engine._h, b"no_such_component"))
