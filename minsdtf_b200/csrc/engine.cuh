@@ -76,7 +76,7 @@ struct Ctx {
   Arena* ws = nullptr;
   bool dry = false;
   int launches = 0;
-  double* gn_stats = nullptr;  // B*64 doubles scratch
+  GnScratch gn;
 
   View alloc_view(int B, int H, int W, int C) {
     View v;
@@ -108,7 +108,7 @@ struct Ctx {
   }
   void groupnorm(const View& x, const NormW& n, bool silu, const View& y) {
     launches += 2;
-    if (!dry) launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn_stats);
+    if (!dry) launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn);
   }
   void layernorm(const View& x, const NormW& n, const View& y) {
     ++launches;

@@ -38,61 +38,97 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // GroupNorm(32 groups, eps 1e-5, biased variance) [+ SiLU]   (reference: keras GroupNormalization at
 // diffusion_model.py:27-28,32-33,57,277-278; layers.py:32,66-79; image_decoder.py:51-52)
 // Phase 1: per-(sample, group) sum / sum-of-squares.  Each thread owns one 8-channel vector position and
-// strides over pixels, so its loads are 16-byte and warp-contiguous; per-channel partials are folded into
-// 32 smem group bins, then one fp64 atomic per bin per CTA.
+// strides over pixels, so its loads are 16-byte and warp-contiguous.  Reduction is DETERMINISTIC and
+// independent of the batch size: per-thread partials -> smem -> 32 threads add them in a fixed order ->
+// one fp64 partial per (CTA, group); the last CTA of a sample (ticket counter) adds the CTA partials in
+// index order and publishes mean / rstd.  The number of CTAs per sample depends only on (H*W, C).
 // Phase 2: normalise + affine (+ SiLU) -> bf16.
 // ------------------------------------------------------------------------------------------------------
+static constexpr int kGnMaxBlk = 64;
+
+struct GnScratch {
+  double* partial = nullptr;    // [B][kGnMaxBlk][64]
+  unsigned* counters = nullptr; // [B], zero between launches (self-resetting)
+  float* stats = nullptr;       // [B][64]: mean, rstd per group
+};
+
 __global__ void __launch_bounds__(512)
-gn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, int pix_per_cta, double* __restrict__ stats) {
+gn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, int pix_per_cta, GnScratch sc) {
+  extern __shared__ float gn_sm[];  // [lanes][C][2]
   const int vecs = C >> 3;
   const int lanes = blockDim.x / vecs;  // pixels processed in parallel by this CTA
   const int cv = threadIdx.x % vecs, pl = threadIdx.x / vecs;
-  const int b = blockIdx.y;
+  const int b = blockIdx.y, nblk = gridDim.x;
   const long long p0 = (long long)blockIdx.x * pix_per_cta;
   const long long p1 = min(HW, p0 + pix_per_cta);
-  __shared__ float bins[64];
-  if (threadIdx.x < 64) bins[threadIdx.x] = 0.f;
-  __syncthreads();
   float s[8], q[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  if (pl < lanes) {
-    const bf16* base = x + ((long long)b * HW) * ld + cv * 8;
-    for (long long p = p0 + pl; p < p1; p += lanes) {
-      const uint4 u = *reinterpret_cast<const uint4*>(base + p * ld);
-      float f[8];
-      unpack8(u, f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        s[i] += f[i];
-        q[i] += f[i] * f[i];
-      }
-    }
-    const int gs = C >> 5;
+  const bf16* base = x + ((long long)b * HW) * ld + cv * 8;
+  for (long long p = p0 + pl; p < p1; p += lanes) {
+    const uint4 u = *reinterpret_cast<const uint4*>(base + p * ld);
+    float f[8];
+    unpack8(u, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int g = (cv * 8 + i) / gs;
-      atomicAdd(&bins[2 * g], s[i]);
-      atomicAdd(&bins[2 * g + 1], q[i]);
+      s[i] += f[i];
+      q[i] += f[i] * f[i];
     }
   }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    gn_sm[((pl * C) + cv * 8 + i) * 2] = s[i];
+    gn_sm[((pl * C) + cv * 8 + i) * 2 + 1] = q[i];
+  }
   __syncthreads();
-  if (threadIdx.x < 64) atomicAdd(&stats[(long long)b * 64 + threadIdx.x], (double)bins[threadIdx.x]);
+  __shared__ bool is_last;
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x, gs = C >> 5;
+    double S = 0, Q = 0;
+    for (int l = 0; l < lanes; ++l)
+      for (int c = g * gs; c < (g + 1) * gs; ++c) {
+        S += gn_sm[(l * C + c) * 2];
+        Q += gn_sm[(l * C + c) * 2 + 1];
+      }
+    double* dst = sc.partial + (((long long)b * kGnMaxBlk + blockIdx.x) * 32 + g) * 2;
+    dst[0] = S;
+    dst[1] = Q;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(&sc.counters[b], 1u);
+    is_last = (ticket == (unsigned)nblk - 1);
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 32) {
+    __threadfence();
+    const int g = threadIdx.x;
+    double S = 0, Q = 0;
+    for (int k = 0; k < nblk; ++k) {
+      const volatile double* src = sc.partial + (((long long)b * kGnMaxBlk + k) * 32 + g) * 2;
+      S += src[0];
+      Q += src[1];
+    }
+    const double n = (double)HW * (C >> 5);
+    const double m = S / n;
+    double var = Q / n - m * m;
+    if (var < 0) var = 0;
+    sc.stats[(long long)b * 64 + 2 * g] = (float)m;
+    sc.stats[(long long)b * 64 + 2 * g + 1] = (float)(1.0 / sqrt(var + 1e-5));
+    if (g == 0) sc.counters[b] = 0;
+  }
 }
 
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, const double* __restrict__ stats,
+gn_apply_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, const float* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu, bf16* __restrict__ y,
                 long long ldy) {
   const int b = blockIdx.y;
   __shared__ float mean[32], rstd[32];
   if (threadIdx.x < 32) {
-    const double n = (double)HW * (C >> 5);
-    const double m = stats[(long long)b * 64 + 2 * threadIdx.x] / n;
-    double var = stats[(long long)b * 64 + 2 * threadIdx.x + 1] / n - m * m;
-    if (var < 0) var = 0;
-    mean[threadIdx.x] = (float)m;
-    rstd[threadIdx.x] = (float)(1.0 / sqrt(var + 1e-5));
+    mean[threadIdx.x] = stats[(long long)b * 64 + 2 * threadIdx.x];
+    rstd[threadIdx.x] = stats[(long long)b * 64 + 2 * threadIdx.x + 1];
   }
   __syncthreads();
   const int vecs = C >> 3, gs = C >> 5;
@@ -120,30 +156,34 @@ gn_apply_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, c
   }
 }
 
-// x: NHWC view (possibly a slice of a wider buffer); y dense [B][HW][C] (ldy may differ); stats: B*64 doubles
+static constexpr int kGnMaxBatch = 256;
+
+// x: NHWC view (possibly a slice of a wider buffer); y dense [B][HW][C] (ldy may differ)
 inline void launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, const float* beta, bool silu, bf16* y,
-                             long long ldy, double* stats) {
+                             long long ldy, const GnScratch& sc) {
   SDTF_CHECK(x.C % 32 == 0 && x.C % 8 == 0, "GroupNorm needs C % 32 == 0");
+  SDTF_CHECK(x.B <= kGnMaxBatch, "GroupNorm: batch too large for the statistics scratch");
   const long long HW = (long long)x.H * x.W;
-  SDTF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 64 * x.B, st));
   const int vecs = x.C / 8;
   int threads = (512 / vecs) * vecs;
-  if (threads == 0) threads = vecs;  // C > 4096 never happens here
-  SDTF_CHECK(threads <= 512, "GroupNorm: too many channels");
-  // enough CTAs to fill 148 SMs a few times over
-  long long want = (148 * 4 + x.B - 1) / x.B;
-  long long ppc = ceil_div_ll(HW, want);
+  SDTF_CHECK(threads >= vecs && threads <= 512, "GroupNorm: unsupported channel count");
   const int lanes = threads / vecs;
-  if (ppc < lanes * 4) ppc = lanes * 4;
-  dim3 g1((unsigned)ceil_div_ll(HW, ppc), (unsigned)x.B);
-  gn_stats_kernel<<<g1, threads, 0, st>>>(x.p, x.ld, x.C, HW, (int)ppc, stats);
+  // CTAs per sample: a function of (HW, C) only, so statistics do not depend on how samples are batched
+  long long nblk = HW / (lanes * 4);
+  if (nblk > kGnMaxBlk) nblk = kGnMaxBlk;
+  if (nblk < 1) nblk = 1;
+  const long long ppc = ceil_div_ll(HW, nblk);
+  nblk = ceil_div_ll(HW, ppc);
+  dim3 g1((unsigned)nblk, (unsigned)x.B);
+  const size_t smem = (size_t)lanes * x.C * 2 * sizeof(float);
+  gn_stats_kernel<<<g1, threads, smem, st>>>(x.p, x.ld, x.C, HW, (int)ppc, sc);
   SDTF_CUDA(cudaGetLastError());
   const long long total = HW * vecs;
   long long blocks = ceil_div_ll(total, 256 * 4);
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
   dim3 g2((unsigned)blocks, (unsigned)x.B);
-  gn_apply_kernel<<<g2, 256, 0, st>>>(x.p, x.ld, x.C, HW, stats, gamma, beta, silu ? 1 : 0, y, ldy);
+  gn_apply_kernel<<<g2, 256, 0, st>>>(x.p, x.ld, x.C, HW, sc.stats, gamma, beta, silu ? 1 : 0, y, ldy);
   SDTF_CUDA(cudaGetLastError());
 }
 
