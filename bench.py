@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="run the resident step --steps times and exit (for ncu)")
     return ap.parse_args()
 
 
@@ -204,6 +205,13 @@ def run_engine(args, rank, world, local_rank):
     def e2e_step():
         return sd.generate_image(ctx, batch_size=B, num_steps=S, unconditional_guidance_scale=7.5, diffusion_noise=noise,
                                  guidance_rescale=0.7, use_cuda_graph=use_graph)
+
+    if args.profile_only:
+        for _ in range(args.warmup + args.steps):
+            resident_step()
+        torch.cuda.synchronize()
+        print(json.dumps({"profile_only": True, "timings": eng.timings()}), flush=True)
+        return
 
     # ---- device-resident arm ----
     for _ in range(args.warmup):
