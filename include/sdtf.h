@@ -153,8 +153,14 @@ int sdtf_get_timings(const sdtf_engine* e, sdtf_timings* out);
 int sdtf_bench_conv(sdtf_engine* e, int32_t batch, int32_t hw, int32_t cin, int32_t cout, int32_t ksize,
                     int32_t reps, float* ms_per_launch);
 
+/* same for the attention kernel: q (batch, nq, heads*d), k/v (batch, nk, heads*d) synthetic; legacy != 0 selects the
+ * one-query-tile-per-CTA kernel (kept for d > 64 and for A/B measurements). */
+int sdtf_bench_attention(sdtf_engine* e, int32_t batch, int32_t heads, int32_t nq, int32_t nk, int32_t d, int32_t reps,
+                         int32_t legacy, float* ms_per_launch);
+
 /* test hooks (used by tests/ only): one kernel each behind the same marshalling.
- * attention: q (B,Nq,heads*d), k/v (B,Nk,heads*d) f32 -> softmax(q k^T d^-1/2) v per head (diffusion_model.py:118-128)
+ * attention: q (B,Nq,heads*d), k/v (B,Nk,heads*d) f32 -> softmax(q k^T d^-1/2) v per head (diffusion_model.py:118-128);
+ *   heads < 0 runs |heads| heads through the legacy one-tile-per-CTA kernel
  * norm: x (B,H,W,C) f32; mode 0 GroupNorm(32), 1 GroupNorm+SiLU, 2 LayerNorm(C); eps 1e-5 */
 int sdtf_test_attention(sdtf_engine* e, const DLManagedTensor* q, const DLManagedTensor* k, const DLManagedTensor* v,
                         int32_t heads, DLManagedTensor* out);

@@ -17,7 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libsdtf.so")
 EXPORTS = [
     "sdtf_create", "sdtf_destroy", "sdtf_last_error", "sdtf_version", "sdtf_load_tensor", "sdtf_finalize_weights",
     "sdtf_unet_forward", "sdtf_controlnet_forward", "sdtf_hintnet_forward", "sdtf_vae_decode", "sdtf_vae_encode",
-    "sdtf_cfg_sched_step", "sdtf_to_uint8", "sdtf_denoise", "sdtf_get_timings", "sdtf_bench_conv",
+    "sdtf_cfg_sched_step", "sdtf_to_uint8", "sdtf_denoise", "sdtf_get_timings", "sdtf_bench_conv", "sdtf_bench_attention",
     "sdtf_test_attention", "sdtf_test_norm",
 ]
 
@@ -75,6 +75,7 @@ def load():
     lib.sdtf_denoise.argtypes = [vp, ctypes.POINTER(DenoiseDesc)]
     lib.sdtf_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
     lib.sdtf_bench_conv.argtypes = [vp, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float)]
+    lib.sdtf_bench_attention.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float)]
     lib.sdtf_test_attention.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.sdtf_test_norm.argtypes = [vp, vp, vp, vp, i32, vp]
     for name in EXPORTS:

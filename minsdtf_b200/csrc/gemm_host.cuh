@@ -3,6 +3,8 @@
 #pragma once
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
+#include <stdlib.h>
 
 namespace sdtf {
 
@@ -31,6 +33,7 @@ struct ConvArgs {
   int act = ACT_NONE;
   float out_scale = 1.f;
   int force_bn = 0;  // testing / tuning
+  bool force_v1 = false;  // one-tile-per-CTA kernel (gemm.cuh) instead of the persistent one (gemm2.cuh)
 };
 
 struct TileShape {
@@ -73,6 +76,32 @@ inline int choose_bn(int N, long long m_tiles, int act) {
 
 inline size_t conv_smem_bytes(int BN, int stages) {
   return 1024 + (size_t)stages * (kATileBytes + (size_t)BN * 128) + 8 * (2 * stages + 1) + 16;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    SDTF_CUDA(cudaGetDevice(&dev));
+    SDTF_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+inline bool gemm_v1_forced() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("SDTF_GEMM_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+static constexpr size_t kSmemLimit = 232448;  // 227 KB per CTA on sm_100
+
+// called once per process before any launch (and before any stream capture)
+inline void init_gemm_kernels() {
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  sm_count();
 }
 
 inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
@@ -120,6 +149,37 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   CUtensorMap tmA1 = a.a1.p ? make_act_tmap(a.a1, p.bw, p.bh, p.bn, a.stride) : tmA0;
   CUtensorMap tmB = make_weight_tmap(w.w, w.K, w.N, p.taps, p.BN);
 
+  // ---- persistent kernel (gemm2.cuh) whenever the output is bf16 and 16-byte chunkable ----
+  {
+    const bool geglu = a.act == ACT_GEGLU;
+    const int ncols = geglu ? p.BN / 2 : p.BN;
+    const int Nout = geglu ? w.N / 2 : w.N;
+    Gemm2Extra x{};
+    x.W = ncols <= 128 ? ncols : ncols / 2;
+    x.passes = ncols <= 128 ? 1 : 2;
+    const bool aligned = Nout % 8 == 0 && a.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                         (a.res == nullptr || (a.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0));
+    if (!a.out_fp32 && !a.force_v1 && !gemm_v1_forced() && aligned && x.W % 16 == 0 && x.W * x.passes == ncols) {
+      x.m_tiles = (int)m_tiles;
+      x.n_tiles = ceil_div(w.N, p.BN);
+      x.pitch = x.W * 2 + 16;
+      int acc = 32;
+      while (acc < p.BN) acc <<= 1;
+      x.acc_stride = acc;
+      p.tmem_cols = 2 * acc;
+      const size_t fixed = 1024 + 2 * (size_t)128 * x.pitch + 1024 + 8 * (2 * 8 + 5) + 16;
+      int st2 = (int)((kSmemLimit - fixed) / stage_bytes);
+      if (st2 > 8) st2 = 8;
+      SDTF_CHECK(st2 >= 2, "gemm2: tile does not fit shared memory");
+      p.stages = st2;
+      const size_t smem2 = 1024 + (size_t)st2 * stage_bytes + 2 * (size_t)128 * x.pitch + 1024 + 8 * (2 * st2 + 5) + 16;
+      const long long total = (long long)x.m_tiles * x.n_tiles;
+      const unsigned grid2 = (unsigned)(total < sm_count() ? total : sm_count());
+      conv_gemm2_kernel<<<grid2, kG2Threads, smem2, stream>>>(tmA0, tmA1, tmB, p, x);
+      SDTF_CUDA(cudaGetLastError());
+      return;
+    }
+  }
   const size_t smem = conv_smem_bytes(p.BN, p.stages);
   static size_t smem_set = 0;
   if (smem > smem_set) {

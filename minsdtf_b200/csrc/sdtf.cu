@@ -211,7 +211,7 @@ int sdtf_create(int32_t device, sdtf_engine** out) {
     SDTF_CUDA(cudaMalloc((void**)&e->step_dev, sizeof(int) * 4));
     for (auto& ev : e->ev) SDTF_CUDA(cudaEventCreate(&ev));
     // kernel attributes are set up-front so that nothing but launches happens under stream capture
-    SDTF_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    init_gemm_kernels();
     init_attn_kernels();
     tensor_map_encoder();
   } catch (const std::exception& ex) {
@@ -797,6 +797,48 @@ int sdtf_bench_conv(sdtf_engine* e, int32_t batch, int32_t hw, int32_t cin, int3
 }
 
 
+int sdtf_bench_attention(sdtf_engine* e, int32_t batch, int32_t heads, int32_t nq, int32_t nk, int32_t d, int32_t reps,
+                         int32_t legacy, float* ms_per_launch) {
+  SDTF_API_BEGIN
+  SDTF_CHECK(ms_per_launch != nullptr && reps >= 1, "bad arguments");
+  float result = 0.f;
+  e->run_sized([&](Ctx& c) {
+    const int dstride = d == 40 ? 64 : d, hs = heads * dstride;
+    // rotate over enough q/k/v/out sets that a launch does not find its operands in L2 (> 126 MB in total)
+    const size_t set_bytes = ((size_t)batch * nq * (hs + heads * d) + (size_t)2 * batch * nk * hs) * 2;
+    int nbuf = (int)((size_t)192 * 1024 * 1024 / (set_bytes ? set_bytes : 1)) + 1;
+    if (nbuf > 8) nbuf = 8;
+    std::vector<AttnArgs> sets;
+    for (int i = 0; i < nbuf; ++i) {
+      AttnArgs a;
+      bf16* q = c.ws->alloc_n<bf16>((size_t)batch * nq * hs);
+      bf16* k = c.ws->alloc_n<bf16>((size_t)batch * nk * hs);
+      bf16* v = c.ws->alloc_n<bf16>((size_t)batch * nk * hs);
+      a.q = q; a.k = k; a.v = v; a.ldq = a.ldk = a.ldv = hs;
+      a.B = batch; a.heads = heads; a.Nq = nq; a.Nk = nk; a.d = d; a.dstride = dstride;
+      a.out = c.ws->alloc_n<bf16>((size_t)batch * nq * heads * d); a.ldo = heads * d;
+      a.legacy = legacy != 0;
+      if (!c.dry) {
+        SDTF_CUDA(cudaMemsetAsync(q, 0x3c, (size_t)batch * nq * hs * 2, e->st));  // bf16 0x3c3c = 0.0115
+        SDTF_CUDA(cudaMemsetAsync(k, 0x3c, (size_t)batch * nk * hs * 2, e->st));
+        SDTF_CUDA(cudaMemsetAsync(v, 0x3c, (size_t)batch * nk * hs * 2, e->st));
+      }
+      sets.push_back(a);
+    }
+    if (c.dry) return;
+    for (int i = 0; i < 3; ++i) c.attention(sets[i % nbuf]);
+    SDTF_CUDA(cudaEventRecord(e->ev[0], e->st));
+    for (int i = 0; i < reps; ++i) c.attention(sets[i % nbuf]);
+    SDTF_CUDA(cudaEventRecord(e->ev[1], e->st));
+    SDTF_CUDA(cudaStreamSynchronize(e->st));
+    float ms = 0;
+    SDTF_CUDA(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+    result = ms / reps;
+  });
+  *ms_per_launch = result;
+  SDTF_API_END
+}
+
 // -------------------------------------------------------------------------------------------------------
 // test hooks: single kernels behind the same marshalling, so tests/ can check them against torch one by one
 // -------------------------------------------------------------------------------------------------------
@@ -817,6 +859,8 @@ int sdtf_test_attention(sdtf_engine* e, const DLManagedTensor* q_t, const DLMana
   TRef q = parse(q_t, "q", e->device), k = parse(k_t, "k", e->device), v = parse(v_t, "v", e->device);
   TRef out = parse(out_t, "out", e->device);
   SDTF_CHECK(q.shape.size() == 3 && k.shape.size() == 3, "q/k/v must be (B,N,heads*d)");
+  const bool legacy = heads < 0;  // negative head count selects the one-tile-per-CTA kernel
+  if (legacy) heads = -heads;
   const int B = (int)q.shape[0], Nq = (int)q.shape[1], C = (int)q.shape[2], Nk = (int)k.shape[1];
   const int d = C / heads, dstride = d == 40 ? 64 : d, hs = heads * dstride;
   expect_shape(k, {B, Nk, C}, "k");
@@ -840,6 +884,7 @@ int sdtf_test_attention(sdtf_engine* e, const DLManagedTensor* q_t, const DLMana
     AttnArgs a;
     a.q = bq; a.k = bk; a.v = bv; a.ldq = a.ldk = a.ldv = hs;
     a.B = B; a.heads = heads; a.Nq = Nq; a.Nk = Nk; a.d = d; a.dstride = dstride; a.out = bo; a.ldo = C;
+    a.legacy = legacy;
     c.attention(a);
     c.cast_out(bo, C, (long long)B * Nq, C, fo);
     e->emit(c, fo, out);

@@ -225,6 +225,11 @@ class Engine:
         self._check(self._lib.sdtf_get_timings(self._h, ctypes.byref(t)))
         return {"loop_ms": t.loop_ms, "decode_ms": t.decode_ms, "total_ms": t.total_ms, "kernel_launches": t.kernel_launches}
 
+    def bench_attention(self, batch, heads, nq, nk, d, reps=20, legacy=False) -> float:
+        ms = ctypes.c_float()
+        self._check(self._lib.sdtf_bench_attention(self._h, batch, heads, nq, nk, d, reps, int(legacy), ctypes.byref(ms)))
+        return float(ms.value)
+
     def bench_conv(self, batch, hw, cin, cout, ksize=3, reps=20) -> float:
         ms = ctypes.c_float()
         self._check(self._lib.sdtf_bench_conv(self._h, batch, hw, cin, cout, ksize, reps, ctypes.byref(ms)))

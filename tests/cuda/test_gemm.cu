@@ -219,6 +219,7 @@ static bool run_case(const Case& c, bool bench) {
 
 int main(int argc, char** argv) {
   bool bench = argc > 1 && !strcmp(argv[1], "bench");
+  init_gemm_kernels();
   std::vector<Case> cases = {
       // name                      B  H   W   C0   C1   N   kh kw s pt pl oH oW  bias temb res  f32  act  bn ldx
       {"linear_64x64x16",          1, 1, 128,  64,   0,  16, 1, 1, 1, 0, 0, 1, 128, false, false, false, true, ACT_NONE, 16, 0},

@@ -39,6 +39,17 @@ def test_conv_gemm_standalone_cases():
     (1, 300, 200, 8, 40),      # ragged queries and keys
 ])
 def test_attention_matches_torch(engine, B, Nq, Nk, heads, d):
+    _check_attention(engine, B, Nq, Nk, heads, d, legacy=False)
+
+
+@pytest.mark.parametrize("B,Nq,Nk,heads,d", [(1, 512, 384, 8, 40), (2, 1024, 77, 8, 40), (1, 9216, 9216, 2, 40)])
+def test_attention_d40_kernels_agree(engine, B, Nq, Nk, heads, d):
+    """the two-query-tile kernel (default for d=40) and the one-tile kernel, each vs torch; 9216 = 96x96 latent (768^2)"""
+    _check_attention(engine, B, Nq, Nk, heads, d, legacy=True)
+    _check_attention(engine, B, Nq, Nk, heads, d, legacy=False)
+
+
+def _check_attention(engine, B, Nq, Nk, heads, d, legacy):
     g = torch.Generator().manual_seed(B * 1000 + Nq + Nk + d)
     C = heads * d
     q = _bf(torch.randn(B, Nq, C, generator=g))
@@ -46,7 +57,8 @@ def test_attention_matches_torch(engine, B, Nq, Nk, heads, d):
     v = _bf(torch.randn(B, Nk, C, generator=g))
     out = np.empty((B, Nq, C), np.float32)
     dl = _lib.DL()
-    engine._check(engine._lib.sdtf_test_attention(engine._h, dl(q.numpy()), dl(k.numpy()), dl(v.numpy()), heads, dl(out)))
+    engine._check(engine._lib.sdtf_test_attention(engine._h, dl(q.numpy()), dl(k.numpy()), dl(v.numpy()),
+                                                   -heads if legacy else heads, dl(out)))
     qh = q.view(B, Nq, heads, d).permute(0, 2, 1, 3).cuda()
     kh = k.view(B, Nk, heads, d).permute(0, 2, 1, 3).cuda()
     vh = v.view(B, Nk, heads, d).permute(0, 2, 1, 3).cuda()
