@@ -71,7 +71,8 @@ inline PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
 // bf16 tensor map, 128-byte swizzle, zero fill out of bounds.  dims/box/estr are innermost-first;
 // strides_bytes[i] is the byte stride of dimension i+1.
 inline CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                  const uint32_t* box, const uint32_t* estr) {
+                                  const uint32_t* box, const uint32_t* estr,
+                                  CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap m;
   SDTF_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16-byte aligned");
   for (int i = 0; i + 1 < rank; ++i)
@@ -81,7 +82,7 @@ inline CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* di
                                     reinterpret_cast<const cuuint64_t*>(strides_bytes),
                                     reinterpret_cast<const cuuint32_t*>(box),
                                     reinterpret_cast<const cuuint32_t*>(estr), CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     std::string s = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") rank " + std::to_string(rank);
@@ -102,6 +103,17 @@ inline CUtensorMap make_act_tmap(const View& v, int bw, int bh, int bn, int stri
   uint32_t box[4] = {64, (uint32_t)(bw * stride), (uint32_t)(bh * stride), (uint32_t)bn};
   uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
   return make_tmap_bf16(v.p, 4, dims, strides, box, es);
+}
+
+// epilogue map over an NHWC output / residual view: dims (C, W, H, B); box (32 channels, bw, bh, bn) = 128 pixels x
+// 64 bytes, 64-byte swizzle (the layout the GEMM epilogue stages its bf16 sub-tiles in).  Stores are clipped and
+// loads zero-filled at the tensor edges by the hardware.
+inline CUtensorMap make_epi_tmap(const bf16* base, int C, int W, int H, int B, long long ld, int bw, int bh, int bn) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+  uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  uint32_t es[4] = {1, 1, 1, 1};
+  return make_tmap_bf16(base, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
 // packed weight map [taps][N][K]: dims (K, N, taps), box (64, BN, 1)

@@ -245,20 +245,20 @@ struct WeightStore {
     for (size_t i = 0; i < ts.size(); ++i) pack_into(pw.w, pw.N, pw.K, (int)i * per, 0, *ts[i], &map, 1.f);
     return pw;
   }
-  // GEGLU projection [8C][C]: rows interleaved per 160-wide N tile as [80 value | 80 gate]
+  // GEGLU projection [8C][C]: rows interleaved per 256-wide N tile as [128 value | 128 gate]
   PackedWeight geglu(const std::string& key) {
     const RawTensor* w = find(key + ".weight");
     PackedWeight pw;
     if (!w) return pw;
     const int N = (int)w->shape[0], half = N / 2;
     std::vector<int> map(N);
-    for (int t = 0; t < N / 160; ++t)
-      for (int j = 0; j < 80; ++j) {
-        map[t * 160 + j] = t * 80 + j;
-        map[t * 160 + 80 + j] = half + t * 80 + j;
+    for (int t = 0; t < N / 256; ++t)
+      for (int j = 0; j < 128; ++j) {
+        map[t * 256 + j] = t * 128 + j;
+        map[t * 256 + 128 + j] = half + t * 128 + j;
       }
     pw = conv(key, true, 1.f, &map);
-    pw.geglu_half = 80;
+    pw.geglu_half = 128;
     return pw;
   }
   void drop_raw(const std::string& prefix) {

@@ -3,7 +3,7 @@
 #pragma once
 #include "common.cuh"
 #include "gemm.cuh"
-#include "gemm2.cuh"
+#include "gemm3.cuh"
 #include <stdlib.h>
 
 namespace sdtf {
@@ -59,7 +59,7 @@ inline TileShape choose_tile(int W, int H, int B) {
 }
 
 inline int choose_bn(int N, long long m_tiles, int act) {
-  if (act == ACT_GEGLU) return 160;
+  if (act == ACT_GEGLU) return 256;
   if (N <= 16) return 16;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
@@ -87,20 +87,82 @@ inline int sm_count() {
   }
   return n;
 }
-inline bool gemm_v1_forced() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("SDTF_GEMM_V1");
-    v = (e && e[0] == '1') ? 1 : 0;
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && e[0]) ? atoi(e) : dflt;
+}
+// SDTF_GEMM = 1: one-tile-per-CTA kernel only (gemm.cuh); 3 (default): persistent TMA-epilogue kernel (gemm3.cuh)
+inline int gemm_version() {
+  static int v = env_int("SDTF_GEMM", 3);
+  return v;
+}
+inline bool gemm_v1_forced() { return gemm_version() == 1; }
+// tuning overrides for experiments: SDTF_GEMM_CG = 1|2 forces the CTA-group size, SDTF_GEMM_BN the N tile
+inline int gemm_force_cg() {
+  static int v = env_int("SDTF_GEMM_CG", 0);
+  return v;
+}
+inline int gemm_force_bn() {
+  static int v = env_int("SDTF_GEMM_BN", 0);
+  return v;
+}
+
+struct G3Plan {
+  int cg = 1, bn = 0;
+};
+// Pick (CTA-group size, BN) for the persistent kernel with a small cost model: waves x k-iteration time, where one
+// k-iteration costs max(tensor-core cycles, operand bytes / L2 delivery rate per SM).
+inline G3Plan plan_gemm3(int N, long long m_tiles, int act, int force_bn) {
+  G3Plan best;
+  if (act == ACT_GEGLU) {
+    best.bn = 256;
+    best.cg = (m_tiles >= 2 && ((m_tiles + 1) / 2) * (N / 256) >= 74) ? 2 : 1;
+    if (gemm_force_cg()) best.cg = (gemm_force_cg() == 2 && m_tiles >= 2) ? 2 : 1;
+    return best;
   }
-  return v == 1;
+  int cands[8], nc = 0;
+  if (force_bn) cands[nc++] = force_bn;
+  else if (gemm_force_bn() && N % gemm_force_bn() == 0) cands[nc++] = gemm_force_bn();
+  else if (N <= 16) cands[nc++] = 16;
+  else if (N <= 32) cands[nc++] = 32;
+  else if (N <= 64) cands[nc++] = 64;
+  else {
+    if (N % 256 == 0) cands[nc++] = 256;
+    if (N % 160 == 0) cands[nc++] = 160;
+    if (N % 128 == 0) cands[nc++] = 128;
+    if (N % 96 == 0) cands[nc++] = 96;
+    if (N % 80 == 0) cands[nc++] = 80;
+    if (N % 64 == 0) cands[nc++] = 64;
+    if (nc == 0) cands[nc++] = N <= 128 ? ((N + 15) / 16) * 16 : 128;  // ragged tail clipped by the TMA store
+  }
+  double best_cost = 1e30;
+  for (int pass = 0; pass < 2 && best.bn == 0; ++pass)
+  for (int i = 0; i < nc; ++i) {
+    const int bn = cands[i];
+    const long long n_tiles = (N + bn - 1) / bn;
+    for (int cg = 1; cg <= 2; ++cg) {
+      if (pass == 0 && gemm_force_cg() && cg != gemm_force_cg()) continue;
+      if (cg == 2 && (m_tiles < 2 || (bn / 2) % 8 != 0)) continue;
+      const long long units = ((m_tiles + cg - 1) / cg) * n_tiles;
+      const long long slots = 148 / cg;
+      const long long waves = (units + slots - 1) / slots;
+      const double busy = (double)(units < slots ? units : slots) * cg / 148.0;  // fraction of SMs pulling from L2
+      const double bytes = 16384.0 + bn * 128.0 / cg;
+      const double l2 = bytes / (60.0 / (busy > 0.25 ? busy : 0.25));
+      const double mma = 2.0 * bn;
+      const double cost = (double)waves * ((mma > l2 ? mma : l2) + 40.0) * (cg == 2 && m_tiles % 2 ? 1.02 : 1.0);
+      if (cost < best_cost) { best_cost = cost; best.cg = cg; best.bn = bn; }
+    }
+  }
+  return best;
 }
 static constexpr size_t kSmemLimit = 232448;  // 227 KB per CTA on sm_100
 
 // called once per process before any launch (and before any stream capture)
 inline void init_gemm_kernels() {
   SDTF_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   sm_count();
 }
 
@@ -123,8 +185,80 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   p.kc0 = ceil_div(a.a0.C, 64);
   p.kc1 = a.a1.p ? ceil_div(a.a1.C, 64) : 0;
   p.N = w.N;
+  p.bias = w.bias;
+  p.temb = a.temb; p.temb_ld = a.temb_ld;
+  p.res = a.res; p.res_ld = a.res_ld;
+  p.out = a.out; p.out_ld = a.out_ld; p.out_fp32 = a.out_fp32 ? 1 : 0;
+  p.act = a.act;
+  p.out_scale = a.out_scale;
+  const bool geglu = a.act == ACT_GEGLU;
+  const int Nout = geglu ? w.N / 2 : w.N;
+  const int iters = p.taps * (p.kc0 + p.kc1);
+
+  // ---- persistent kernel (gemm3.cuh) whenever the output is bf16 and TMA-addressable ----
+  const bool aligned = Nout % 8 == 0 && a.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
+                       (a.res == nullptr || (a.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0));
+  if (!a.out_fp32 && !a.force_v1 && !gemm_v1_forced() && aligned) {
+    const G3Plan plan = plan_gemm3(w.N, m_tiles, a.act, a.force_bn);
+    p.BN = plan.bn;
+    const int ncols = geglu ? p.BN / 2 : p.BN;
+    const int n_tiles = ceil_div(w.N, p.BN);
+    // a last pass narrower than 32 columns is shifted back over columns the tile already wrote: fine unless the
+    // residual is read from the tensor being written
+    const bool overlap_ok = ncols % 32 == 0 || ncols < 32 || a.res != a.out;
+    if (ncols % 32 == 0 || (ncols < 32 && n_tiles == 1) || (ncols > 32 && overlap_ok)) {
+      if (geglu) SDTF_CHECK(w.geglu_half * 2 == p.BN && w.N % p.BN == 0, "GEGLU weight packing must match BN");
+      Gemm3Extra x{};
+      x.m_tiles = (int)m_tiles;
+      x.n_tiles = n_tiles;
+      x.ncols = ncols;
+      int acc = 32;
+      while (acc < p.BN) acc <<= 1;
+      x.acc_stride = acc;
+      p.tmem_cols = 2 * acc;
+      int lg = 0;
+      while ((1 << lg) < p.bw * p.bh) ++lg;
+      x.log_rows_per_b = lg;
+      const int cg = plan.cg;
+      const size_t stage_bytes = kATileBytes + (size_t)(p.BN / cg) * 128;
+      const size_t fixed = 1024 + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * 10 + 4 + kG3Bufs) + 16;
+      int st = (int)((kSmemLimit - fixed) / stage_bytes);
+      if (st > 10) st = 10;
+      if (st > iters) st = iters < 2 ? 2 : iters;
+      SDTF_CHECK(st >= 2, "gemm3: tile does not fit shared memory");
+      p.stages = st;
+      const size_t smem = 1024 + (size_t)st * stage_bytes + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * st + 4 + kG3Bufs) + 16;
+      CUtensorMap tmA0 = make_act_tmap(a.a0, p.bw, p.bh, p.bn, a.stride);
+      CUtensorMap tmA1 = a.a1.p ? make_act_tmap(a.a1, p.bw, p.bh, p.bn, a.stride) : tmA0;
+      CUtensorMap tmB = make_weight_tmap(w.w, w.K, w.N, p.taps, p.BN / cg);
+      CUtensorMap tmOut = make_epi_tmap(reinterpret_cast<const bf16*>(a.out), Nout, p.W, p.H, p.B, a.out_ld, p.bw, p.bh, p.bn);
+      CUtensorMap tmRes = a.res ? make_epi_tmap(a.res, Nout, p.W, p.H, p.B, a.res_ld, p.bw, p.bh, p.bn) : tmOut;
+      const long long units = ((m_tiles + cg - 1) / cg) * n_tiles;
+      const long long slots = sm_count() / cg;
+      const unsigned grid = (unsigned)((units < slots ? units : slots) * cg);
+      if (cg == 2) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kG3Threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SDTF_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm3_kernel<2>, tmA0, tmA1, tmB, tmOut, tmRes, p, x));
+      } else {
+        conv_gemm3_kernel<1><<<grid, kG3Threads, smem, stream>>>(tmA0, tmA1, tmB, tmOut, tmRes, p, x);
+      }
+      SDTF_CUDA(cudaGetLastError());
+      return;
+    }
+  }
+
+  // ---- one tile per CTA (gemm.cuh): fp32 outputs, unaligned views ----
   p.BN = a.force_bn ? a.force_bn : choose_bn(w.N, m_tiles, a.act);
-  if (a.act == ACT_GEGLU) SDTF_CHECK(w.geglu_half * 2 == p.BN && w.N % p.BN == 0, "GEGLU weight packing must match BN");
+  if (geglu) SDTF_CHECK(w.geglu_half * 2 == p.BN && w.N % p.BN == 0, "GEGLU weight packing must match BN");
   SDTF_CHECK(p.BN % 16 == 0 && p.BN >= 16 && p.BN <= 256, "BN must be a multiple of 16 in [16,256]");
   int cols = 32;
   while (cols < p.BN) cols <<= 1;
@@ -135,57 +269,12 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   int stages = (int)((110 * 1024) / stage_bytes);
   if (stages > 6) stages = 6;
   if (stages < 2) stages = 2;
-  const int iters = p.taps * (p.kc0 + p.kc1);
   if (stages > iters) stages = iters < 1 ? 1 : iters;
   p.stages = stages;
-  p.bias = w.bias;
-  p.temb = a.temb; p.temb_ld = a.temb_ld;
-  p.res = a.res; p.res_ld = a.res_ld;
-  p.out = a.out; p.out_ld = a.out_ld; p.out_fp32 = a.out_fp32 ? 1 : 0;
-  p.act = a.act;
-  p.out_scale = a.out_scale;
-
   CUtensorMap tmA0 = make_act_tmap(a.a0, p.bw, p.bh, p.bn, a.stride);
   CUtensorMap tmA1 = a.a1.p ? make_act_tmap(a.a1, p.bw, p.bh, p.bn, a.stride) : tmA0;
   CUtensorMap tmB = make_weight_tmap(w.w, w.K, w.N, p.taps, p.BN);
-
-  // ---- persistent kernel (gemm2.cuh) whenever the output is bf16 and 16-byte chunkable ----
-  {
-    const bool geglu = a.act == ACT_GEGLU;
-    const int ncols = geglu ? p.BN / 2 : p.BN;
-    const int Nout = geglu ? w.N / 2 : w.N;
-    Gemm2Extra x{};
-    x.W = ncols <= 128 ? ncols : ncols / 2;
-    x.passes = ncols <= 128 ? 1 : 2;
-    const bool aligned = Nout % 8 == 0 && a.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
-                         (a.res == nullptr || (a.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0));
-    if (!a.out_fp32 && !a.force_v1 && !gemm_v1_forced() && aligned && x.W % 16 == 0 && x.W * x.passes == ncols) {
-      x.m_tiles = (int)m_tiles;
-      x.n_tiles = ceil_div(w.N, p.BN);
-      x.pitch = x.W * 2 + 16;
-      int acc = 32;
-      while (acc < p.BN) acc <<= 1;
-      x.acc_stride = acc;
-      p.tmem_cols = 2 * acc;
-      const size_t fixed = 1024 + 2 * (size_t)128 * x.pitch + 1024 + 8 * (2 * 8 + 5) + 16;
-      int st2 = (int)((kSmemLimit - fixed) / stage_bytes);
-      if (st2 > 8) st2 = 8;
-      SDTF_CHECK(st2 >= 2, "gemm2: tile does not fit shared memory");
-      p.stages = st2;
-      const size_t smem2 = 1024 + (size_t)st2 * stage_bytes + 2 * (size_t)128 * x.pitch + 1024 + 8 * (2 * st2 + 5) + 16;
-      const long long total = (long long)x.m_tiles * x.n_tiles;
-      const unsigned grid2 = (unsigned)(total < sm_count() ? total : sm_count());
-      conv_gemm2_kernel<<<grid2, kG2Threads, smem2, stream>>>(tmA0, tmA1, tmB, p, x);
-      SDTF_CUDA(cudaGetLastError());
-      return;
-    }
-  }
   const size_t smem = conv_smem_bytes(p.BN, p.stages);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    SDTF_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    smem_set = 200 * 1024;
-  }
   dim3 grid((unsigned)m_tiles, (unsigned)ceil_div(w.N, p.BN), 1);
   conv_gemm_kernel<<<grid, 128, smem, stream>>>(tmA0, tmA1, tmB, p);
   SDTF_CUDA(cudaGetLastError());

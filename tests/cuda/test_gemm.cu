@@ -138,7 +138,7 @@ static bool run_case(const Case& c, bool bench) {
 
   PackedWeight pw;
   pw.w = w; pw.bias = bias; pw.K = Kp; pw.N = c.N; pw.kh = c.kh; pw.kw = c.kw;
-  pw.geglu_half = c.act == ACT_GEGLU ? 80 : 0;
+  pw.geglu_half = c.act == ACT_GEGLU ? 128 : 0;
   ConvArgs a;
   a.a0 = View{a0, c.B, c.H, c.W, c.C0, ld0};
   if (c.C1) a.a1 = View{a1, c.B, c.H, c.W, c.C1, ld1};
@@ -219,6 +219,7 @@ static bool run_case(const Case& c, bool bench) {
 
 int main(int argc, char** argv) {
   bool bench = argc > 1 && !strcmp(argv[1], "bench");
+  const char* only = argc > 2 ? argv[2] : nullptr;  // bench <substr>: run only the benchmark cases whose name contains substr
   init_gemm_kernels();
   std::vector<Case> cases = {
       // name                      B  H   W   C0   C1   N   kh kw s pt pl oH oW  bias temb res  f32  act  bn ldx
@@ -240,6 +241,12 @@ int main(int argc, char** argv) {
       {"conv3x3_96x96",            1, 96, 96, 64,   0,  64, 3, 3, 1, 1, 1, 96, 96, true, false, false, false, ACT_NONE, 0, 0},
       {"conv3x3_12x12_b3",         3, 12, 12, 64,   0,  64, 3, 3, 1, 1, 1, 12, 12, true, false, false, false, ACT_NONE, 0, 0},
       {"conv3x3_c16_silu",         1, 64, 64,  16,  0,  32, 3, 3, 1, 1, 1, 64, 64, true, false, false, false, ACT_SILU, 0, 0},
+      {"conv3x3_n16_hint",         1, 64, 64,   8,  0,  16, 3, 3, 1, 1, 1, 64, 64, true, false, false, false, ACT_SILU, 0, 0},
+      {"conv3x3_24x24_b2_res",     2, 24, 24, 128,  0, 320, 3, 3, 1, 1, 1, 24, 24, true, true, true, false, ACT_NONE, 0, 0},
+      {"linear_n512_k320",         1, 1, 1000, 320,   0, 512, 1, 1, 1, 0, 0, 1, 1000, false, false, false, false, ACT_NONE, 0, 0},
+      {"linear_n1280_bn80_res",    1, 1, 1024, 1280,  0, 1280, 1, 1, 1, 0, 0, 1, 1024, true, false, true, false, ACT_NONE, 80, 0},
+      {"linear_geglu_m1000",       1, 1, 1000, 640,   0, 5120, 1, 1, 1, 0, 0, 1, 1000, true, false, false, false, ACT_GEGLU, 0, 0},
+      {"conv3x3_96ch_slice_res",   2, 32, 32,  96,  0,  96, 3, 3, 1, 1, 1, 32, 32, true, false, true, false, ACT_NONE, 0, 32},
   };
   std::vector<Case> bench_cases = {
       {"b16_conv3x3_64_320",      16, 64, 64, 320,  0, 320, 3, 3, 1, 1, 1, 64, 64, true, true, false, false, ACT_NONE, 0, 0},
@@ -250,6 +257,10 @@ int main(int argc, char** argv) {
       {"b16_geglu_4096x320",       1, 1, 65536, 320, 0, 2560, 1, 1, 1, 0, 0, 1, 65536, true, false, false, false, ACT_GEGLU, 0, 0},
       {"b16_ff2_4096x1280",        1, 1, 65536, 1280, 0, 320, 1, 1, 1, 0, 0, 1, 65536, true, false, true, false, ACT_NONE, 0, 0},
       {"b16_linear_1024x640",      1, 1, 16384, 640, 0, 640, 1, 1, 1, 0, 0, 1, 16384, true, false, true, false, ACT_NONE, 0, 0},
+      {"b16_linear_4096x320_res",  1, 1, 65536, 320, 0, 320, 1, 1, 1, 0, 0, 1, 65536, true, false, true, false, ACT_NONE, 0, 0},
+      {"b16_qkv_4096x320",         1, 1, 65536, 320, 0, 1536, 1, 1, 1, 0, 0, 1, 65536, false, false, false, false, ACT_NONE, 0, 0},
+      {"b16_qkv_1024x640",         1, 1, 16384, 640, 0, 1920, 1, 1, 1, 0, 0, 1, 16384, false, false, false, false, ACT_NONE, 0, 0},
+      {"b16_geglu_1024x640",       1, 1, 16384, 640, 0, 5120, 1, 1, 1, 0, 0, 1, 16384, true, false, false, false, ACT_GEGLU, 0, 0},
       {"b2_conv3x3_64_320",        2, 64, 64, 320,  0, 320, 3, 3, 1, 1, 1, 64, 64, true, true, false, false, ACT_NONE, 0, 0},
       {"b2_conv3x3_16_1280",       2, 16, 16, 1280, 0, 1280, 3, 3, 1, 1, 1, 16, 16, true, true, false, false, ACT_NONE, 0, 0},
       {"vae_b4_conv3x3_512_128",   4, 512, 512, 128, 0, 128, 3, 3, 1, 1, 1, 512, 512, true, false, false, false, ACT_NONE, 0, 0},
@@ -257,9 +268,11 @@ int main(int argc, char** argv) {
   };
   int fails = 0;
   try {
-    for (auto& c : cases) fails += run_case(c, false) ? 0 : 1;
+    if (!only)
+      for (auto& c : cases) fails += run_case(c, false) ? 0 : 1;
     if (bench)
-      for (auto& c : bench_cases) fails += run_case(c, true) ? 0 : 1;
+      for (auto& c : bench_cases)
+        if (!only || strstr(c.name, only)) fails += run_case(c, true) ? 0 : 1;
   } catch (const std::exception& e) {
     printf("EXCEPTION: %s\n", e.what());
     return 2;

@@ -1,7 +1,7 @@
 #!/bin/bash
-# full GPU test-suite + engine bench (no reference arm, no ncu)
+# full GPU test-suite + engine bench + kernel micro-benchmarks (no reference arm, no ncu)
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee gpurun_out/gpu_tests.log
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/gpu_tests.log
 python bench.py --steps 3 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_engine.json 2> gpurun_out/bench_engine.err
 tail -3 gpurun_out/bench_engine.err
 python - <<'PY'
@@ -9,3 +9,4 @@ import json
 j=json.load(open('gpurun_out/bench_engine.json'))
 print({k:j[k] for k in ('value','ms_per_step','unet_step_ms','unet_step_tflops','decode_ms_per_batch','gpu_launches','clocks')}, j['e2e'], j['roofline']['achieved'])
 PY
+python tools/bench_kernels.py all 2>&1 | tee gpurun_out/bench_kernels.jsonl
