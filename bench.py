@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="run the resident step --steps times and exit (for ncu)")
+    ap.add_argument("--no-cfg-split", action="store_true", help="skip the extra CFG-split (GPU pairs + NCCL) measurement at N >= 2")
     return ap.parse_args()
 
 
@@ -238,6 +239,37 @@ def run_engine(args, rank, world, local_rank):
     wall_e2e = time.perf_counter() - t0
     assert out.shape == (B, size, size, 3) and out.dtype == np.uint8
 
+    # ---- CFG-split variant (N >= 2, even): GPU pairs, each rank one CFG branch, one ncclAllGather of eps per step ----
+    split_info = None
+    if world >= 2 and world % 2 == 0 and not args.no_cfg_split:
+        from minsdtf_b200 import dist as D
+        plan = D.setup_cfg_split(eng, rank, world, device=dev)
+        Bp = 2 * B  # prompts per pair: every GPU still runs a UNet batch of 2B per step, as in the data-parallel arm
+        p_noise = torch.as_tensor(synth.latents(Bp, h, h, seed=223456 + plan.pair)).to(dev)
+        p_ctx = torch.as_tensor(synth.context(Bp, 77, seed=223457 + plan.pair)).to(dev)
+        p_unc = torch.as_tensor(synth.uncond_context(Bp, 77)).to(dev)
+        half = slice(plan.branch * B, (plan.branch + 1) * B)
+
+        def split_step():
+            lat = eng.denoise(p_noise, p_ctx, p_unc, d_temb, coefs, decode=False, use_cuda_graph=use_graph, cfg_split=True)
+            return eng.to_uint8(eng.vae_decode(lat[half].contiguous()))  # each member decodes its half of the pair's images
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            split_step()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            imgs = split_step()
+        barrier()
+        wall_split = time.perf_counter() - t0
+        ts = torch.tensor([wall_split], dtype=torch.float64, device=dev)
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        split_info = {"value": Bp * (world // 2) * args.steps / ts.item(), "unit": "images/s", "ms_per_step": ts.item() / args.steps * 1e3,
+                      "pairs": world // 2, "prompts_per_pair": Bp, "exchange": "ncclAllGather of eps (B,64,64,4) f32 per step, in-graph",
+                      "timing": "host wall clock around K generations incl. barrier (max over ranks)"}
+        assert tuple(imgs.shape) == (B, size, size, 3)
+
     # ---- max over ranks ----
     t = torch.tensor([dev_ms, wall, wall_e2e, loop_ms, dec_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -271,10 +303,12 @@ def run_engine(args, rank, world, local_rank):
             "unet_step_ms": unet_step_ms, "unet_step_tflops": unet_tflops, "unet_step_frac_of_peak": unet_tflops / peak,
             "decode_ms_per_batch": dec_ms / K, "wall_ms_per_step": wall / K * 1e3,
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
-                         "traffic": None, "kernel": "conv_gemm_kernel 3x3 320->320 @64x64, batch %d" % (2 * B),
+                         "traffic": None, "kernel": "conv_gemm3_kernel 3x3 320->320 @64x64, batch %d" % (2 * B),
                          "flop_per_launch": CONV_GFLOP * 2 * B * 1e9, "ms_per_launch": conv_ms, "peak_source": peak_src},
             "clocks": clocks,
         }
+        if split_info is not None:
+            line["cfg_split"] = split_info
         if not args.skip_cpu_baseline and world == 1:
             v, cores, sample, _, _ = cpu_reference_rate(S, size)
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}

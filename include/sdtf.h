@@ -76,7 +76,9 @@ typedef struct {
   int32_t n_steps;
   int32_t use_cuda_graph;                  /* 1: capture one step, replay it n_steps times */
   int32_t decode;                          /* 1: run the VAE decoder and produce uint8 images */
-  int32_t reserved;
+  int32_t cfg_split;                       /* 1: 2-way CFG split over the engine's communicator (sdtf_comm_init): this
+                                              rank evaluates one branch (rank 0 uncond, rank 1 cond) and the epsilons
+                                              are exchanged with one ncclAllGather per step */
   const DLManagedTensor* latent0;          /* (B,h,w,4) f32 start latent (noise, or noised init for img2img) */
   const DLManagedTensor* context;          /* (B,T,768) f32 */
   const DLManagedTensor* uncond_context;   /* (B,T,768) f32, NULL when guidance == 0 */
@@ -146,6 +148,13 @@ int sdtf_to_uint8(sdtf_engine* e, const DLManagedTensor* decoded, const DLManage
 /* the whole generate_image loop on the device */
 int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d);
 int sdtf_get_timings(const sdtf_engine* e, sdtf_timings* out);
+
+/* 2-way CFG split (the reference has no multi-device path).  libnccl is dlopen'ed from `nccl_lib`
+ * (NULL: $SDTF_NCCL_LIB, then the default soname).  sdtf_comm_unique_id fills 128 bytes on one rank; the caller ships
+ * them to its partner (any transport) and both call sdtf_comm_init(engine, lib, id, rank, 2). */
+int sdtf_comm_unique_id(const char* nccl_lib, void* out_id128);
+int sdtf_comm_init(sdtf_engine* e, const char* nccl_lib, const void* id128, int32_t rank, int32_t world);
+int sdtf_comm_destroy(sdtf_engine* e);
 
 /* kernel micro-benchmarks used by bench.py for the roofline line: runs `reps` launches of one representative
  * contraction of the UNet (3x3 conv, batch*hw x cin -> cout) on device-resident synthetic data and returns the

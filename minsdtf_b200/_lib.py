@@ -18,7 +18,7 @@ EXPORTS = [
     "sdtf_create", "sdtf_destroy", "sdtf_last_error", "sdtf_version", "sdtf_load_tensor", "sdtf_finalize_weights",
     "sdtf_unet_forward", "sdtf_controlnet_forward", "sdtf_hintnet_forward", "sdtf_vae_decode", "sdtf_vae_encode",
     "sdtf_cfg_sched_step", "sdtf_to_uint8", "sdtf_denoise", "sdtf_get_timings", "sdtf_bench_conv", "sdtf_bench_attention",
-    "sdtf_test_attention", "sdtf_test_norm",
+    "sdtf_test_attention", "sdtf_test_norm", "sdtf_comm_unique_id", "sdtf_comm_init", "sdtf_comm_destroy",
 ]
 
 
@@ -29,7 +29,7 @@ class StepCoef(ctypes.Structure):
 
 class DenoiseDesc(ctypes.Structure):
     _fields_ = [("n_steps", ctypes.c_int32), ("use_cuda_graph", ctypes.c_int32), ("decode", ctypes.c_int32),
-                ("reserved", ctypes.c_int32),
+                ("cfg_split", ctypes.c_int32),
                 ("latent0", ctypes.c_void_p), ("context", ctypes.c_void_p), ("uncond_context", ctypes.c_void_p),
                 ("t_emb", ctypes.c_void_p), ("coefs", ctypes.POINTER(StepCoef)), ("step_noise", ctypes.c_void_p),
                 ("mask", ctypes.c_void_p), ("init_latent", ctypes.c_void_p), ("init_noise", ctypes.c_void_p),
@@ -76,6 +76,9 @@ def load():
     lib.sdtf_get_timings.argtypes = [vp, ctypes.POINTER(Timings)]
     lib.sdtf_bench_conv.argtypes = [vp, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float)]
     lib.sdtf_bench_attention.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, ctypes.POINTER(ctypes.c_float)]
+    lib.sdtf_comm_unique_id.argtypes = [ctypes.c_char_p, vp]
+    lib.sdtf_comm_init.argtypes = [vp, ctypes.c_char_p, vp, i32, i32]
+    lib.sdtf_comm_destroy.argtypes = [vp]
     lib.sdtf_test_attention.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.sdtf_test_norm.argtypes = [vp, vp, vp, vp, i32, vp]
     for name in EXPORTS:

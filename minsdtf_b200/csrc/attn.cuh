@@ -287,8 +287,8 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
     for (int s = 0; s < VST; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
     for (int g = 0; g < 2; ++g) {
-      mbar_init(s_full(g), 1); mbar_init(s_empty(g), 128);
-      mbar_init(p_full(g), 128); mbar_init(o_done(g), 1);
+      mbar_init(s_full(g), 1); mbar_init(s_empty(g), 4);  // one arrive per softmax warp (128 per-thread arrives on one
+      mbar_init(p_full(g), 4); mbar_init(o_done(g), 1);   // barrier serialise as shared-memory atomics)
     }
     fence_mbar_init();
   }
@@ -389,7 +389,8 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       tmem_ld32_at<96>(tS + 96, sv);
       tmem_ld_wait();
       fence_before_sync();
-      mbar_arrive(s_empty(g));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(g));
       if (nk_valid < 128) {
 #pragma unroll
         for (int i = 0; i < 128; ++i)
@@ -440,7 +441,8 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       l_run += lsum0 + lsum1;
       fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
       fence_before_sync();
-      mbar_arrive(p_full(g));
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(g));
     }
     // ---- epilogue: O / l -> bf16 ----
     mbar_wait(o_done(g), (uint32_t)(nkv - 1) & 1u);

@@ -71,6 +71,26 @@ struct NormW {
 // ----------------------------------------------------------------------------------------------------------
 // Launch context
 // ----------------------------------------------------------------------------------------------------------
+// Timing ablation (debug only; results are garbage): SDTF_SKIP=conv,attn,gn,ln,misc makes the listed kernel classes
+// no-ops, so the in-graph cost of a class is (step time without the flag) - (step time with it).
+enum : int { SKIP_CONV = 1, SKIP_ATTN = 2, SKIP_GN = 4, SKIP_LN = 8, SKIP_MISC = 16 };
+inline int skip_mask() {
+  static int m = -1;
+  if (m < 0) {
+    m = 0;
+    const char* e = getenv("SDTF_SKIP");
+    if (e) {
+      const std::string v = e;
+      if (v.find("conv") != std::string::npos) m |= SKIP_CONV;
+      if (v.find("attn") != std::string::npos) m |= SKIP_ATTN;
+      if (v.find("gn") != std::string::npos) m |= SKIP_GN;
+      if (v.find("ln") != std::string::npos) m |= SKIP_LN;
+      if (v.find("misc") != std::string::npos) m |= SKIP_MISC;
+    }
+  }
+  return m;
+}
+
 struct Ctx {
   cudaStream_t st = nullptr;
   Arena* ws = nullptr;
@@ -87,7 +107,7 @@ struct Ctx {
 
   void conv(const ConvArgs& a) {
     ++launches;
-    if (!dry) launch_conv(st, a);
+    if (!dry && !(skip_mask() & SKIP_CONV)) launch_conv(st, a);
   }
   // y = conv(x) (+bias) (+temb) (+res) ; out view may be a channel slice
   void conv(const View& x, const PackedWeight& w, const View& out, int stride = 1, int pad = -1, const View* res = nullptr,
@@ -108,19 +128,19 @@ struct Ctx {
   }
   void groupnorm(const View& x, const NormW& n, bool silu, const View& y) {
     launches += 2;
-    if (!dry) launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn);
+    if (!dry && !(skip_mask() & SKIP_GN)) launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn);
   }
   void layernorm(const View& x, const NormW& n, const View& y) {
     ++launches;
-    if (!dry) launch_layernorm(st, x.p, x.ld, x.C, x.pixels(), n.gamma, n.beta, y.p, y.ld);
+    if (!dry && !(skip_mask() & SKIP_LN)) launch_layernorm(st, x.p, x.ld, x.C, x.pixels(), n.gamma, n.beta, y.p, y.ld);
   }
   void attention(const AttnArgs& a) {
     ++launches;
-    if (!dry) launch_attn(st, a);
+    if (!dry && !(skip_mask() & SKIP_ATTN)) launch_attn(st, a);
   }
   void upsample2x(const View& x, const View& y) {
     ++launches;
-    if (!dry) launch_upsample2x(st, x, y.p);
+    if (!dry && !(skip_mask() & SKIP_MISC)) launch_upsample2x(st, x, y.p);
   }
   void add_inplace(const View& y, const bf16* c) {
     ++launches;

@@ -10,9 +10,14 @@
 //   * the epilogue no longer computes addresses: accumulator rows go TMEM -> registers -> bf16 into a 64-byte-swizzled
 //     128 x 32 staging tile, which leaves as ONE TMA tensor store (clipped at the tensor edges by the hardware);
 //     residual tiles arrive the same way (TMA load into the staging buffer two passes ahead, summed in place).
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (pair: leader CTA only) and TMEM owner, warps 2-5 = epilogue.
-// Pipelines: smem ring full/empty (TMA <-> MMA), two TMEM accumulators tfull/tempty (MMA <-> epilogue), four
-// staging buffers tracked with bulk async-groups (epilogue <-> TMA store) and res_full barriers (TMA load -> epilogue).
+//   * N tiles wider than one MMA (BN up to 512 = two N <= 256 instructions on the same A stage) cut the bytes per
+//     FLOP further; above 256 columns the accumulator is single-buffered (512 TMEM columns), which long-K convs
+//     amortise.  Measured (ncu, 3x3 conv): tensor pipe 50 % busy at 256x160 tiles, 80 % at 256x256 — the L2 -> SM
+//     path delivers ~50 B/clk/SM, so tile area per byte is what sets the rate.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (pair: leader CTA only) and TMEM owner, warps 2-5 = epilogue,
+// warp 6 = store warp (TMA stores of staged sub-tiles, residual prefetch / buffer grants).
+// Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulators tfull/tempty (MMA <-> epilogue), four staging
+// buffers: grant (res_bar: buffer free, residual landed) -> epilogue -> stg_full -> store warp -> bulk-group wait.
 #pragma once
 #include "gemm.cuh"
 
@@ -23,22 +28,39 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ float gelu_tanh_fast(float g) {
   const float u = g * 0.7978845608f * (1.f + 0.044715f * g * g);
   return 0.5f * g * (1.f + tanh_approx(u));
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 struct Gemm3Extra {
   int m_tiles, n_tiles;  // 128-row M tiles, BN-wide N tiles
-  int acc_stride;        // TMEM column distance between the two accumulator stages
+  int acc_stride;        // TMEM column distance between accumulator stages
+  int acc_bufs;          // 2: double-buffered accumulator (BN <= 256), 1: single (BN up to 512)
+  int n_mma;             // MMA instructions along N per k-step (BN / n_mma columns each, <= 256)
   int ncols;             // output columns per tile (BN, or BN/2 for GEGLU)
   int log_rows_per_b;    // log2(bw*bh): tile row >> this = sample offset inside the tile
+  int vec_rows;          // rows of the per-tile epilogue vector staged in smem: samples a tile spans (time-embedding conv) or 1
+  int vec_width;         // its width in floats (tile columns, rounded up to 32)
+  long long* prof;       // optional [gridDim.x][16] cycle counters per role (null: off); see gemm_host.cuh
+  int debug;             // timing experiments only (results are garbage): 1 = skip the MMA instructions, 2 = skip the TMA loads
 };
 
-static constexpr int kG3Threads = 192;
+// cycle accounting for the role loops (only when x.prof is set): t += clock spent inside a wait
+#define G3_TIMED(prof_on, acc, stmt)            \
+  do {                                          \
+    if (prof_on) {                              \
+      const long long _t0 = clock64();          \
+      stmt;                                     \
+      acc += clock64() - _t0;                   \
+    } else {                                    \
+      stmt;                                     \
+    }                                           \
+  } while (0)
+
+static constexpr int kG3Threads = 224;
 static constexpr int kG3Bufs = 4;                 // staging buffers
-static constexpr int kG3ResAhead = 2;             // residual prefetch distance (passes)
 static constexpr uint32_t kG3BufBytes = 128 * 64; // 128 rows x 32 bf16
 
 template <int CG>
@@ -60,7 +82,9 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * p.stages + 2 + a); };
   auto res_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + 4 + b); };
-  const uint32_t slot_off = bar_off + 8u * (2 * p.stages + 4 + kG3Bufs);
+  auto stg_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + 4 + kG3Bufs + b); };
+  const uint32_t slot_off = bar_off + 8u * (2 * p.stages + 4 + 2 * kG3Bufs);
+  const uint32_t vec_off = slot_off + 16u;  // float [2][vec_rows][vec_width]: bias (+ time-embedding) of the current tile
   const uint32_t tmem_slot = smem_base + slot_off;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + slot_off);
 
@@ -72,6 +96,9 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int m_units = (x.m_tiles + CG - 1) / CG;
   const int total_units = m_units * x.n_tiles;
   const int unit0 = (int)blockIdx.x / CG, unit_step = (int)gridDim.x / CG;
+  const bool prof_on = x.prof != nullptr;
+  long long* prof = prof_on ? x.prof + (long long)blockIdx.x * 16 : nullptr;
+  const long long t_start = prof_on ? clock64() : 0;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA0);
@@ -85,9 +112,12 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128 * CG);
+      mbar_init(tempty_bar(a), 4 * CG);  // one arrive per epilogue warp
     }
-    for (int b = 0; b < kG3Bufs; ++b) mbar_init(res_bar(b), 1);
+    for (int b = 0; b < kG3Bufs; ++b) {
+      mbar_init(res_bar(b), 1);
+      mbar_init(stg_bar(b), 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -112,72 +142,156 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 0) {
     if (elect_one()) {
       // ===== TMA producer =====
-      int it = 0;
+      // (one thread: everything per k-iteration is kept incremental — no divisions, no address rebuilds; measured:
+      //  the naive loop cost ~570 cycles per iteration of scalar work and was the bottleneck of the whole kernel)
+      long long w_empty = 0;
+      uint32_t st = 0, ph = 0;  // ring slot and the parity of its current fill
+      uint32_t sa = smem_base, fb = full_bar(0), eb = empty_bar(0);
+      const uint32_t chunk_rows = b_rows / (uint32_t)x.n_mma;  // weight rows per MMA chunk held by this CTA
+      const uint32_t chunk_stride = chunk_rows * 128u;
+      const int chunk = p.BN / x.n_mma;
+      const uint32_t tx_bytes = (uint32_t)CG * stage_bytes;
+      const uint32_t n_stages = (uint32_t)p.stages;
       for (int u = unit0; u < total_units; u += unit_step) {
         int n_tile, x0, y0, b0;
         tile_coords(u, n_tile, x0, y0, b0);
-        const int nrow0 = n_tile * p.BN + (int)(rank * b_rows);
+        const int nrow0 = n_tile * p.BN + (int)(rank * chunk_rows);
+        const int cx0 = x0 * p.stride - p.pad_x, cy0 = y0 * p.stride - p.pad_y;
+        int r = 0, sx = 0;
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int r = tap / p.tap_w, s = tap - r * p.tap_w;
-          const int cx = x0 * p.stride + s - p.pad_x;
-          const int cy = y0 * p.stride + r - p.pad_y;
-          for (int kc = 0; kc < kchunks; ++kc, ++it) {
-            const int st = it % p.stages;
-            const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-            mbar_wait(empty_bar(st), ph ^ 1u);
-            const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
+          const int cx = cx0 + sx, cy = cy0 + r;
+          for (int kc = 0; kc < kchunks; ++kc) {
+            G3_TIMED(prof_on, w_empty, mbar_wait(eb, ph ^ 1u));
             const uint32_t sb = sa + kATileBytes;
-            if (CG == 1) {
-              mbar_expect_tx(full_bar(st), stage_bytes);
-              if (kc < p.kc0) tma_load_4d(sa, &tmA0, full_bar(st), kc * kBK, cx, cy, b0);
-              else            tma_load_4d(sa, &tmA1, full_bar(st), (kc - p.kc0) * kBK, cx, cy, b0);
-              tma_load_3d(sb, &tmB, full_bar(st), kc * kBK, nrow0, tap);
+            const CUtensorMap* ta = kc < p.kc0 ? &tmA0 : &tmA1;
+            const int ka = (kc < p.kc0 ? kc : kc - p.kc0) * kBK;
+            if (x.debug & 2) {
+              if (rank == 0) mbar_arrive(fb);
+            } else if (CG == 1) {
+              mbar_expect_tx(fb, tx_bytes);
+              tma_load_4d(sa, ta, fb, ka, cx, cy, b0);
+              tma_load_3d(sb, &tmB, fb, kc * kBK, nrow0, tap);
+              if (x.n_mma == 2) tma_load_3d(sb + chunk_stride, &tmB, fb, kc * kBK, nrow0 + chunk, tap);
             } else {
-              if (rank == 0) mbar_expect_tx(full_bar(st), 2u * stage_bytes);  // both CTAs' bytes land on the leader's barrier
-              if (kc < p.kc0) tma_load_4d_pair(sa, &tmA0, full_bar(st), kc * kBK, cx, cy, b0);
-              else            tma_load_4d_pair(sa, &tmA1, full_bar(st), (kc - p.kc0) * kBK, cx, cy, b0);
-              tma_load_3d_pair(sb, &tmB, full_bar(st), kc * kBK, nrow0, tap);
+              if (rank == 0) mbar_expect_tx(fb, tx_bytes);  // both CTAs' bytes land on the leader's barrier
+              tma_load_4d_pair(sa, ta, fb, ka, cx, cy, b0);
+              tma_load_3d_pair(sb, &tmB, fb, kc * kBK, nrow0, tap);
+              if (x.n_mma == 2) tma_load_3d_pair(sb + chunk_stride, &tmB, fb, kc * kBK, nrow0 + chunk, tap);
             }
+            sa += stage_bytes; fb += 8u; eb += 8u;
+            if (++st == n_stages) { st = 0; ph ^= 1u; sa = smem_base; fb = full_bar(0); eb = empty_bar(0); }
           }
+          if (++sx == p.tap_w) { sx = 0; ++r; }
         }
       }
+      if (prof_on) { prof[0] = w_empty; prof[1] = clock64() - t_start; }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
       // ===== MMA issuer (pair: leader CTA only) =====
-      const uint32_t idesc = make_idesc_bf16(kBM * CG, p.BN, 0, 0);
-      int it = 0, lt = 0;
-      for (int u = unit0; u < total_units; u += unit_step, ++lt) {
-        const int acc = lt & 1;
-        mbar_wait(tempty_bar(acc), ((uint32_t)(lt >> 1) & 1u) ^ 1u);  // both CTAs' epilogues drained this accumulator
+      const int chunk = p.BN / x.n_mma;
+      const uint32_t idesc = make_idesc_bf16(kBM * CG, chunk, 0, 0);
+      // UMMA descriptors differ between ring slots / k-steps / N chunks only in their 14-bit start-address field
+      // (bytes >> 4), so they are built once and advanced by integer adds
+      const uint64_t da0 = make_smem_desc_sw128(smem_base, 16, 1024);
+      const uint64_t db0 = make_smem_desc_sw128(smem_base + kATileBytes, 16, 1024);
+      const uint64_t stage_step = (uint64_t)(stage_bytes >> 4);
+      const uint64_t chunk_step = (uint64_t)(((uint32_t)(chunk / CG) * 128u) >> 4);
+      const uint32_t n_stages = (uint32_t)p.stages;
+      const bool two = x.n_mma == 2, skip = (x.debug & 1) != 0;
+      long long w_full = 0, w_tempty = 0;
+      uint32_t st = 0, ph = 0;
+      uint32_t fb = full_bar(0), eb = empty_bar(0);
+      uint64_t da = da0, db = db0;
+      uint32_t acc = 0, acc_ph = 0;
+      for (int u = unit0; u < total_units; u += unit_step) {
+        // both CTAs' epilogues drained this accumulator
+        G3_TIMED(prof_on, w_tempty, mbar_wait(tempty_bar(acc), acc_ph ^ 1u));
         fence_after_sync();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * x.acc_stride);
-        for (int i = 0; i < iters; ++i, ++it) {
-          const int st = it % p.stages;
-          const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-          mbar_wait(full_bar(st), ph);
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)x.acc_stride;
+        const uint32_t d_tmem2 = d_tmem + (uint32_t)chunk;
+        for (int i = 0; i < iters; ++i) {
+          G3_TIMED(prof_on, w_full, mbar_wait(fb, ph));
           fence_after_sync();
-          const uint32_t sa = smem_base + (uint32_t)st * stage_bytes;
-          const uint32_t sb = sa + kATileBytes;
+          if (!skip) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            if (CG == 2) mma_f16_ss_pair(d_tmem, da, db, idesc, (i | k) != 0);
-            else mma_f16_ss(d_tmem, da, db, idesc, (i | k) != 0);
+            for (int k = 0; k < kBK / 16; ++k) {
+              const uint32_t accum = (i | k) != 0;
+              if (CG == 2) {
+                mma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                if (two) mma_f16_ss_pair(d_tmem2, da + 2 * k, db + chunk_step + 2 * k, idesc, accum);
+              } else {
+                mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, accum);
+                if (two) mma_f16_ss(d_tmem2, da + 2 * k, db + chunk_step + 2 * k, idesc, accum);
+              }
+            }
           }
-          if (CG == 2) mma_commit_pair(empty_bar(st)); else mma_commit(empty_bar(st));
+          if (CG == 2) mma_commit_pair(eb); else mma_commit(eb);
+          da += stage_step; db += stage_step; fb += 8u; eb += 8u;
+          if (++st == n_stages) { st = 0; ph ^= 1u; da = da0; db = db0; fb = full_bar(0); eb = empty_bar(0); }
         }
         if (CG == 2) mma_commit_pair(tfull_bar(acc)); else mma_commit(tfull_bar(acc));
+        if (++acc == (uint32_t)x.acc_bufs) { acc = 0; acc_ph ^= 1u; }
       }
+      if (prof_on) { prof[2] = w_full; prof[3] = w_tempty; prof[4] = clock64() - t_start; }
+    }
+    __syncwarp();
+  } else if (warp == 6) {
+    // ===== store warp: TMA stores of staged sub-tiles; grants staging buffers (with the residual tile when there is one)
+    if (elect_one()) {
+      const bool geglu = (p.act == ACT_GEGLU);
+      const int ncols = x.ncols;
+      const int passes = (ncols + 31) >> 5;
+      const bool has_res = p.res != nullptr;
+      auto pass_col = [&](int ps) { return (ps * 32 + 32 <= ncols || ncols < 32) ? ps * 32 : ncols - 32; };
+      (void)geglu;
+      const int my_units = unit0 < total_units ? (total_units - unit0 + unit_step - 1) / unit_step : 0;
+      const int total_passes = my_units * passes;
+      // grant cursor: pass gg = (unit gu, pass gps) may use buffer gg % kG3Bufs
+      int gu = unit0, gps = 0, gg = 0;
+      auto grant = [&]() {
+        if (gg >= total_passes) return;
+        const int buf = gg % kG3Bufs;
+        if (has_res) {
+          int n_tile, x0, y0, b0;
+          tile_coords(gu, n_tile, x0, y0, b0);
+          mbar_expect_tx(res_bar(buf), kG3BufBytes);
+          tma_load_4d(smem_base + stg_off + (uint32_t)buf * kG3BufBytes, &tmRes, res_bar(buf), n_tile * ncols + pass_col(gps),
+                      x0, y0, b0);
+        } else {
+          mbar_arrive(res_bar(buf));
+        }
+        ++gg;
+        if (++gps == passes) { gps = 0; gu += unit_step; }
+      };
+      for (int k = 0; k < kG3Bufs; ++k) grant();
+      long long w_stg = 0, w_read = 0;
+      int sg = 0;
+      for (int u = unit0; u < total_units; u += unit_step) {
+        int n_tile, x0, y0, b0;
+        tile_coords(u, n_tile, x0, y0, b0);
+        for (int ps = 0; ps < passes; ++ps, ++sg) {
+          const int buf = sg % kG3Bufs;
+          // all 4 epilogue warps staged (and fenced) their rows
+          G3_TIMED(prof_on, w_stg, mbar_wait(stg_bar(buf), (uint32_t)(sg / kG3Bufs) & 1u));
+          tma_store_4d(&tmOut, smem_base + stg_off + (uint32_t)buf * kG3BufBytes, n_tile * ncols + pass_col(ps), x0, y0, b0);
+          bulk_commit();
+          if (sg >= 1) {
+            // store sg-1 no longer reads its buffer: it can host pass sg-1+kG3Bufs
+            G3_TIMED(prof_on, w_read, bulk_wait_read<1>());
+            grant();
+          }
+        }
+      }
+      bulk_wait_all();
+      if (prof_on) { prof[5] = w_stg; prof[6] = w_read; prof[7] = clock64() - t_start; }
     }
     __syncwarp();
   } else {
     // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
-    const bool issuer = (threadIdx.x == 64);
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const bool geglu = (p.act == ACT_GEGLU);
     const int ncols = x.ncols;
@@ -187,36 +301,56 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int sw = (row >> 1) & 3;  // 64-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
     auto pass_col = [&](int ps) { return (ps * 32 + 32 <= ncols || ncols < 32) ? ps * 32 : ncols - 32; };
 
-    // residual prefetch cursor (issuer only): pass pf_g = (unit pf_u, pass pf_ps)
-    int pf_u = unit0, pf_ps = 0, pf_g = 0;
-    auto issue_res = [&]() {
-      if (pf_u >= total_units) return;
-      int n_tile, x0, y0, b0;
-      tile_coords(pf_u, n_tile, x0, y0, b0);
-      const int buf = pf_g % kG3Bufs;
-      mbar_expect_tx(res_bar(buf), kG3BufBytes);
-      tma_load_4d(smem_base + stg_off + (uint32_t)buf * kG3BufBytes, &tmRes, res_bar(buf), n_tile * ncols + pass_col(pf_ps), x0,
-                  y0, b0);
-      ++pf_g;
-      if (++pf_ps == passes) { pf_ps = 0; pf_u += unit_step; }
-    };
-    if (has_res && issuer)
-      for (int k = 0; k < kG3ResAhead; ++k) issue_res();
-
+    long long w_tfull = 0, w_grant = 0;
+    const int et = (int)threadIdx.x - 64;  // 0..127
+    const bool has_vec = p.bias != nullptr || p.temb != nullptr;
+    const int vrows = x.vec_rows, vwidth = x.vec_width;
+    const int Nvec = geglu ? p.N : Nout;
+    float* vec = reinterpret_cast<float*>(smem_gen + vec_off);
     int lt = 0, g = 0;
     for (int u = unit0; u < total_units; u += unit_step, ++lt) {
       int n_tile, x0, y0, b0;
       tile_coords(u, n_tile, x0, y0, b0);
-      const int acc = lt & 1;
+      const int acc = lt % x.acc_bufs;
       const uint32_t t_row = tmem_base + (uint32_t)(acc * x.acc_stride) + lane_off;
-      int ob = b0 + (row >> x.log_rows_per_b);
-      ob = ob < p.B ? ob : p.B - 1;
-      mbar_wait(tfull_bar(acc), (uint32_t)(lt >> 1) & 1u);
+      int vr = row >> x.log_rows_per_b;  // sample of this row inside the tile
+      vr = vr < vrows ? vr : vrows - 1;
+      // this tile's per-column vector (bias, + the time-embedding row of each sample the tile spans): fetched from
+      // global BEFORE waiting for the accumulator so the latency hides behind the main loop, then staged in smem
+      float4 pre[4];
+      const int vcol = 4 * et;
+      if (has_vec && vcol < vwidth) {
+        const int gcol = n_tile * (geglu ? p.BN : ncols) + vcol;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < vrows && gcol < Nvec) {
+            if (p.bias) a = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+            if (p.temb) {
+              int bb = b0 + r;
+              bb = bb < p.B ? bb : p.B - 1;
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.temb + (long long)bb * p.temb_ld + gcol));
+              a.x += t4.x; a.y += t4.y; a.z += t4.z; a.w += t4.w;
+            }
+          }
+          pre[r] = a;
+        }
+      }
+      G3_TIMED(prof_on, w_tfull, mbar_wait(tfull_bar(acc), (uint32_t)(lt / x.acc_bufs) & 1u));
       fence_after_sync();
+      float* vtile = vec + (size_t)(lt & 1) * vrows * vwidth;
+      if (has_vec) {
+        if (vcol < vwidth) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            if (r < vrows) *reinterpret_cast<float4*>(vtile + r * vwidth + vcol) = pre[r];
+        }
+        epi_bar_sync();  // vector visible to all four warps; also: everyone is done reading the tile before last's copy
+      }
+      const float* vrow = vtile + vr * vwidth;
       for (int ps = 0; ps < passes; ++ps, ++g) {
         const int buf = g % kG3Bufs;
         const int tc = pass_col(ps);          // column inside the tile's output slice
-        const int col = n_tile * ncols + tc;  // global output column
         uint32_t v[32];
         float f[32];
         tmem_ld32(t_row + (uint32_t)tc, v);
@@ -224,13 +358,12 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           uint32_t gv[32];
           tmem_ld32(t_row + (uint32_t)(ncols + tc), gv);
           tmem_ld_wait();
-          const float* bp = p.bias + n_tile * p.BN + tc;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
-            if (p.bias) {
-              bv = __ldg(reinterpret_cast<const float4*>(bp + i));
-              bg = __ldg(reinterpret_cast<const float4*>(bp + ncols + i));
+            if (has_vec) {
+              bv = *reinterpret_cast<const float4*>(vrow + tc + i);
+              bg = *reinterpret_cast<const float4*>(vrow + ncols + tc + i);
             }
             f[i] = (__uint_as_float(v[i]) + bv.x) * gelu_tanh_fast(__uint_as_float(gv[i]) + bg.x);
             f[i + 1] = (__uint_as_float(v[i + 1]) + bv.y) * gelu_tanh_fast(__uint_as_float(gv[i + 1]) + bg.y);
@@ -241,40 +374,25 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.out_scale;
-          if (col + 32 <= Nout) {
-            if (p.bias) {
+          if (has_vec) {
 #pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + col + i));
-                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
-              }
-            }
-            if (p.temb) {
-              const float* tp = p.temb + (long long)ob * p.temb_ld + col;
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) {
-                const float4 tv = __ldg(reinterpret_cast<const float4*>(tp + i));
-                f[i] += tv.x; f[i + 1] += tv.y; f[i + 2] += tv.z; f[i + 3] += tv.w;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (col + i < Nout) {
-                if (p.bias) f[i] += __ldg(p.bias + col + i);
-                if (p.temb) f[i] += __ldg(p.temb + (long long)ob * p.temb_ld + col + i);
-              }
+            for (int i = 0; i < 32; i += 4) {
+              const float4 bv = *reinterpret_cast<const float4*>(vrow + tc + i);
+              f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
             }
           }
         }
         if (ps + 1 == passes) {  // accumulator fully read: hand it back to the MMA warp (of the leader CTA)
           fence_before_sync();
-          if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
-          else mbar_arrive(tempty_bar(acc));
+          __syncwarp();
+          if (lane == 0) {  // (an arrive per thread would serialise 128 shared-memory atomics on one barrier)
+            if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+            else mbar_arrive(tempty_bar(acc));
+          }
         }
         uint8_t* my_row = smem_gen + stg_off + (uint32_t)buf * kG3BufBytes + (uint32_t)row * 64u;
+        G3_TIMED(prof_on, w_grant, mbar_wait(res_bar(buf), (uint32_t)(g / kG3Bufs) & 1u));  // buffer granted (residual landed)
         if (has_res) {
-          mbar_wait(res_bar(buf), (uint32_t)(g / kG3Bufs) & 1u);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint4 r4 = *reinterpret_cast<const uint4*>(my_row + ((c ^ sw) << 4));
@@ -300,21 +418,12 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           o.w = pack_bf16(f[8 * c + 6], f[8 * c + 7]);
           *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) = o;
         }
-        fence_proxy_async_smem();  // staged tile (generic proxy) -> visible to the TMA store (async proxy)
-        // without residual loads gating the buffers: the store that last used the NEXT pass's buffer must be done reading
-        if (!has_res && issuer) bulk_wait_read<kG3Bufs - 2>();
-        epi_bar_sync();
-        if (issuer) {
-          tma_store_4d(&tmOut, smem_base + stg_off + (uint32_t)buf * kG3BufBytes, col, x0, y0, b0);
-          bulk_commit();
-          if (has_res) {
-            bulk_wait_read<kG3Bufs - kG3ResAhead>();  // buffer of pass g + ResAhead is free again
-            issue_res();
-          }
-        }
+        fence_proxy_async_smem();  // staged row (generic proxy) -> visible to the TMA store (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(stg_bar(buf));
       }
     }
-    if (issuer) bulk_wait_all();
+    if (prof_on && threadIdx.x == 64) { prof[8] = w_tfull; prof[9] = w_grant; prof[10] = clock64() - t_start; prof[11] = lt; }
   }
 
   // teardown: everyone (in both CTAs of a pair) done with TMEM before the allocating warp frees it

@@ -6,6 +6,8 @@
 #include "gemm3.cuh"
 #include <stdlib.h>
 
+#include <vector>
+
 namespace sdtf {
 
 // Packed weight as the kernel wants it: [taps][N][K] bf16 (K contiguous), plus fp32 bias.
@@ -108,52 +110,56 @@ inline int gemm_force_bn() {
 }
 
 struct G3Plan {
-  int cg = 1, bn = 0;
+  int cg = 1, bn = 0, n_mma = 1, bufs = 2;
 };
-// Pick (CTA-group size, BN) for the persistent kernel with a small cost model: waves x k-iteration time, where one
-// k-iteration costs max(tensor-core cycles, operand bytes / L2 delivery rate per SM).
-inline G3Plan plan_gemm3(int N, long long m_tiles, int act, int force_bn) {
+// Pick (CTA-group size, N tile) for the persistent kernel with a small cost model.  One k-iteration (64 channels of
+// one tap) costs max(tensor cycles = 2*BN, operand bytes / L2->SM delivery rate); measured delivery is ~50 B/clk/SM
+// with every SM pulling (ncu: 256x160 tiles keep the tensor pipe 50 % busy, 256x256 tiles 80 %).  Tiles wider than
+// 256 columns are two MMAs per k-step and a single-buffered accumulator: their epilogue is not hidden.
+inline G3Plan plan_gemm3(int N, long long m_tiles, int act, int force_bn, int iters) {
   G3Plan best;
-  if (act == ACT_GEGLU) {
-    best.bn = 256;
-    best.cg = (m_tiles >= 2 && ((m_tiles + 1) / 2) * (N / 256) >= 74) ? 2 : 1;
-    if (gemm_force_cg()) best.cg = (gemm_force_cg() == 2 && m_tiles >= 2) ? 2 : 1;
-    return best;
-  }
-  int cands[8], nc = 0;
-  if (force_bn) cands[nc++] = force_bn;
+  int cands[40], nc = 0;
+  const bool geglu = act == ACT_GEGLU;
+  if (geglu) cands[nc++] = 256;
+  else if (force_bn) cands[nc++] = force_bn;
   else if (gemm_force_bn() && N % gemm_force_bn() == 0) cands[nc++] = gemm_force_bn();
   else if (N <= 16) cands[nc++] = 16;
   else if (N <= 32) cands[nc++] = 32;
   else if (N <= 64) cands[nc++] = 64;
   else {
-    if (N % 256 == 0) cands[nc++] = 256;
-    if (N % 160 == 0) cands[nc++] = 160;
-    if (N % 128 == 0) cands[nc++] = 128;
-    if (N % 96 == 0) cands[nc++] = 96;
+    for (int bn = 512; bn >= 64; bn -= 32)
+      if (N % bn == 0 && (bn <= 256 || bn % 64 == 0)) cands[nc++] = bn;
     if (N % 80 == 0) cands[nc++] = 80;
-    if (N % 64 == 0) cands[nc++] = 64;
     if (nc == 0) cands[nc++] = N <= 128 ? ((N + 15) / 16) * 16 : 128;  // ragged tail clipped by the TMA store
   }
   double best_cost = 1e30;
   for (int pass = 0; pass < 2 && best.bn == 0; ++pass)
-  for (int i = 0; i < nc; ++i) {
-    const int bn = cands[i];
-    const long long n_tiles = (N + bn - 1) / bn;
-    for (int cg = 1; cg <= 2; ++cg) {
-      if (pass == 0 && gemm_force_cg() && cg != gemm_force_cg()) continue;
-      if (cg == 2 && (m_tiles < 2 || (bn / 2) % 8 != 0)) continue;
-      const long long units = ((m_tiles + cg - 1) / cg) * n_tiles;
-      const long long slots = 148 / cg;
-      const long long waves = (units + slots - 1) / slots;
-      const double busy = (double)(units < slots ? units : slots) * cg / 148.0;  // fraction of SMs pulling from L2
-      const double bytes = 16384.0 + bn * 128.0 / cg;
-      const double l2 = bytes / (60.0 / (busy > 0.25 ? busy : 0.25));
-      const double mma = 2.0 * bn;
-      const double cost = (double)waves * ((mma > l2 ? mma : l2) + 40.0) * (cg == 2 && m_tiles % 2 ? 1.02 : 1.0);
-      if (cost < best_cost) { best_cost = cost; best.cg = cg; best.bn = bn; }
+    for (int i = 0; i < nc; ++i) {
+      const int bn = cands[i];
+      const long long n_tiles = (N + bn - 1) / bn;
+      const int n_mma = bn > 256 ? 2 : 1;
+      for (int cg = 1; cg <= 2; ++cg) {
+        if (pass == 0 && gemm_force_cg() && cg != gemm_force_cg()) continue;
+        if (cg == 2 && (m_tiles < 2 || (bn / n_mma / 2) % 8 != 0)) continue;
+        if ((bn / n_mma) % 16 != 0) continue;
+        const size_t stage = 16384 + (size_t)bn * 128 / cg;
+        if (3 * stage + 40000 > 232448) continue;  // at least 3 stages
+        const long long units = ((m_tiles + cg - 1) / cg) * n_tiles;
+        const long long slots = 148 / cg;
+        const long long waves = (units + slots - 1) / slots;
+        const double busy = (double)(units < slots ? units : slots) * cg / 148.0;  // fraction of SMs pulling from L2
+        const double rate = 50.0 / (busy > 0.3 ? busy : 0.3);
+        const double mma = 2.0 * bn;
+        const double l2 = (double)stage / rate;
+        const double t_iter = (mma > l2 ? mma : l2) + 30.0;
+        const int ncols = geglu ? bn / 2 : bn;
+        const double t_epi = 300.0 + ((ncols + 31) / 32) * 280.0;
+        const double t_main = iters * t_iter;
+        const double t_unit = bn > 256 ? t_main + t_epi : (t_main > t_epi ? t_main : t_epi) + 200.0;
+        const double cost = (double)waves * t_unit * (cg == 2 && m_tiles % 2 ? 1.02 : 1.0);
+        if (cost < best_cost) { best_cost = cost; best.cg = cg; best.bn = bn; best.n_mma = n_mma; best.bufs = bn > 256 ? 1 : 2; }
+      }
     }
-  }
   return best;
 }
 static constexpr size_t kSmemLimit = 232448;  // 227 KB per CTA on sm_100
@@ -199,14 +205,15 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   const bool aligned = Nout % 8 == 0 && a.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
                        (a.res == nullptr || (a.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0));
   if (!a.out_fp32 && !a.force_v1 && !gemm_v1_forced() && aligned) {
-    const G3Plan plan = plan_gemm3(w.N, m_tiles, a.act, a.force_bn);
+    const G3Plan plan = plan_gemm3(w.N, m_tiles, a.act, a.force_bn, iters);
     p.BN = plan.bn;
     const int ncols = geglu ? p.BN / 2 : p.BN;
     const int n_tiles = ceil_div(w.N, p.BN);
     // a last pass narrower than 32 columns is shifted back over columns the tile already wrote: fine unless the
     // residual is read from the tensor being written
     const bool overlap_ok = ncols % 32 == 0 || ncols < 32 || a.res != a.out;
-    if (ncols % 32 == 0 || (ncols < 32 && n_tiles == 1) || (ncols > 32 && overlap_ok)) {
+    const bool vec_ok = a.temb == nullptr || p.bn <= 4;  // the staged epilogue vector holds up to 4 sample rows
+    if (vec_ok && (ncols % 32 == 0 || (ncols < 32 && n_tiles == 1) || (ncols > 32 && overlap_ok))) {
       if (geglu) SDTF_CHECK(w.geglu_half * 2 == p.BN && w.N % p.BN == 0, "GEGLU weight packing must match BN");
       Gemm3Extra x{};
       x.m_tiles = (int)m_tiles;
@@ -215,27 +222,43 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       int acc = 32;
       while (acc < p.BN) acc <<= 1;
       x.acc_stride = acc;
-      p.tmem_cols = 2 * acc;
+      x.acc_bufs = plan.bufs;
+      x.n_mma = plan.n_mma;
+      p.tmem_cols = plan.bufs * acc;
+      SDTF_CHECK(p.tmem_cols <= 512, "gemm3: accumulators exceed TMEM");
       int lg = 0;
       while ((1 << lg) < p.bw * p.bh) ++lg;
       x.log_rows_per_b = lg;
+      x.vec_rows = a.temb ? p.bn : 1;
+      x.vec_width = ((geglu ? p.BN : ncols) + 31) / 32 * 32;
+      const size_t vec_bytes = (size_t)2 * x.vec_rows * x.vec_width * 4;
       const int cg = plan.cg;
       const size_t stage_bytes = kATileBytes + (size_t)(p.BN / cg) * 128;
-      const size_t fixed = 1024 + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * 10 + 4 + kG3Bufs) + 16;
+      const size_t fixed = 1024 + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * 10 + 4 + 2 * kG3Bufs) + 32 + vec_bytes;
       int st = (int)((kSmemLimit - fixed) / stage_bytes);
       if (st > 10) st = 10;
       if (st > iters) st = iters < 2 ? 2 : iters;
       SDTF_CHECK(st >= 2, "gemm3: tile does not fit shared memory");
       p.stages = st;
-      const size_t smem = 1024 + (size_t)st * stage_bytes + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * st + 4 + kG3Bufs) + 16;
+      const size_t smem = 1024 + (size_t)st * stage_bytes + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * st + 4 + 2 * kG3Bufs) + 32 + vec_bytes;
       CUtensorMap tmA0 = make_act_tmap(a.a0, p.bw, p.bh, p.bn, a.stride);
       CUtensorMap tmA1 = a.a1.p ? make_act_tmap(a.a1, p.bw, p.bh, p.bn, a.stride) : tmA0;
-      CUtensorMap tmB = make_weight_tmap(w.w, w.K, w.N, p.taps, p.BN / cg);
+      CUtensorMap tmB = make_weight_tmap(w.w, w.K, w.N, p.taps, p.BN / plan.n_mma / cg);
       CUtensorMap tmOut = make_epi_tmap(reinterpret_cast<const bf16*>(a.out), Nout, p.W, p.H, p.B, a.out_ld, p.bw, p.bh, p.bn);
       CUtensorMap tmRes = a.res ? make_epi_tmap(a.res, Nout, p.W, p.H, p.B, a.res_ld, p.bw, p.bh, p.bn) : tmOut;
       const long long units = ((m_tiles + cg - 1) / cg) * n_tiles;
       const long long slots = sm_count() / cg;
       const unsigned grid = (unsigned)((units < slots ? units : slots) * cg);
+      // SDTF_GEMM_PROFILE=1: per-role wait-cycle accounting, printed after the launch (debug; synchronises)
+      static const int profile = env_int("SDTF_GEMM_PROFILE", 0);
+      static const int debug = env_int("SDTF_GEMM_DEBUG", 0);
+      x.debug = debug;
+      static long long* prof_buf = nullptr;
+      if (profile) {
+        if (!prof_buf) SDTF_CUDA(cudaMalloc((void**)&prof_buf, sizeof(long long) * 16 * 160));
+        SDTF_CUDA(cudaMemsetAsync(prof_buf, 0, sizeof(long long) * 16 * 160, stream));
+        x.prof = prof_buf;
+      }
       if (cg == 2) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(grid);
@@ -252,6 +275,23 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
         conv_gemm3_kernel<1><<<grid, kG3Threads, smem, stream>>>(tmA0, tmA1, tmB, tmOut, tmRes, p, x);
       }
       SDTF_CUDA(cudaGetLastError());
+      if (profile) {
+        SDTF_CUDA(cudaStreamSynchronize(stream));
+        std::vector<long long> h(16 * 160);
+        SDTF_CUDA(cudaMemcpy(h.data(), prof_buf, sizeof(long long) * 16 * 160, cudaMemcpyDeviceToHost));
+        double a[16] = {0};
+        for (unsigned b = 0; b < grid; ++b)
+          for (int k = 0; k < 16; ++k) a[k] += (double)h[b * 16 + k] / grid;
+        fprintf(stderr,
+                "[gemm3-prof] N %d iters %d CG %d BN %d | producer wait_empty %.0f / %.0f | mma wait_full %.0f wait_tempty %.0f / %.0f | "
+                "store wait_stg %.0f wait_read %.0f / %.0f | epi wait_tfull %.0f wait_grant %.0f / %.0f tiles %.1f (cycles, avg per CTA; "
+                "mma counters are per leader CTA x1/CG)\n",
+                w.N, iters, cg, p.BN, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]);
+      }
+      static const int verbose = env_int("SDTF_GEMM_VERBOSE", 0);
+      if (verbose)
+        fprintf(stderr, "[gemm3] M-tiles %lld N %d K-iters %d -> CG %d BN %d (x%d MMA, %d acc) stages %d grid %u\n", m_tiles, w.N,
+                iters, cg, p.BN, plan.n_mma, plan.bufs, st, grid);
       return;
     }
   }

@@ -152,6 +152,14 @@ inline void build_time(WeightStore& ws, const std::string& p, TimeW& t, std::vec
     if (w && bi) {
       ws.pack_into(t.wcat, total, kTimeDim, off, 0, *w, nullptr, 1.f);
       ws.pack_vec(*bi, nullptr, 1.f, t.bcat, off);
+      // fold the bias of the conv that consumes this projection (in_layers.2, diffusion_model.py:29,48) into the table:
+      // its epilogue then adds ONE per-(sample, channel) vector instead of two
+      ResW* r = b.second;
+      if (r->c1.bias) {
+        vec_add_kernel<<<ceil_div(r->cout, 256), 256, 0, ws.st>>>(t.bcat + off, r->c1.bias, r->cout);
+        SDTF_CUDA(cudaGetLastError());
+        r->c1.bias = nullptr;
+      }
     }
     b.second->temb_off = off;
     off += b.second->cout;

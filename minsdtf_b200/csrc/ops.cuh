@@ -530,6 +530,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int I, int tap
   }
 }
 
+__global__ void vec_add_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
 __global__ void gather_f32_kernel(const float* __restrict__ src, const int* __restrict__ row_map, int n, float scale,
                                   float* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

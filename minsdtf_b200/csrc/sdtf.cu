@@ -9,6 +9,7 @@
 #include <cstring>
 #include <functional>
 
+#include "comm.cuh"
 #include "models.cuh"
 
 using namespace sdtf;
@@ -103,6 +104,8 @@ struct sdtf_engine {
   Arena ws;
   GnScratch gn;
   int* step_dev = nullptr;
+  Comm comm;
+  const char* nccl_path = nullptr;
   sdtf_timings timings{};
   cudaEvent_t ev[4]{};
   // captured step graph
@@ -228,6 +231,10 @@ void sdtf_destroy(sdtf_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->st);
   e->drop_graph();
+  if (e->comm.comm) {
+    try { nccl_api(nullptr).CommDestroy(e->comm.comm); } catch (...) {}
+    e->comm.comm = nullptr;
+  }
   for (auto& kv : e->weights.raw) cudaFree(kv.second.p);
   if (e->ws.base) cudaFree(e->ws.base);
   cudaFree(e->gn.partial);
@@ -571,6 +578,9 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
   const int T = (int)ctx.shape[1];
   expect_shape(temb, {S, 320}, "t_emb");
   const bool cfg = d->uncond_context != nullptr && d->coefs[0].guidance > 0.f;
+  const bool split = d->cfg_split != 0;
+  if (split) SDTF_CHECK(cfg && e->comm.active() && e->comm.world == 2, "cfg_split needs guidance > 0 and a 2-rank communicator (sdtf_comm_init)");
+  const int srank = split ? e->comm.rank : 0;
   TRef uctx, snoise, mask, initl, initn, hint_img, bimg, bmask, oimg, olat;
   if (cfg) { uctx = parse(d->uncond_context, "uncond_context", e->device); expect_shape(uctx, {B, T, kCtxDim}, "uncond_context"); }
   if (d->step_noise) { snoise = parse(d->step_noise, "step_noise", e->device); expect_shape(snoise, {S, B, h, w, 4}, "step_noise"); }
@@ -600,10 +610,11 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
   if (d->out_latent) { olat = parse(d->out_latent, "out_latent", e->device); expect_shape(olat, {B, h, w, 4}, "out_latent"); }
   std::vector<StepCoef> coefs(S);
   for (int i = 0; i < S; ++i) coefs[i] = to_coef(d->coefs[i]);
-  const int Bt = cfg ? 2 * B : B;
+  const int Bt = (cfg && !split) ? 2 * B : B;  // samples per UNet pass on THIS rank
+  const bool dup = cfg && !split;              // uncond | cond halves batched into one pass
   const int n = h * w * 4;
   const std::string key = std::to_string(B) + "x" + std::to_string(h) + "x" + std::to_string(w) + "x" + std::to_string(T) +
-                          (cfg ? "c" : "-") + (control ? "n" : "-") + (inpaint ? "m" : "-") + (d->step_noise ? "z" : "-") +
+                          (cfg ? (split ? (srank ? "S" : "s") : "c") : "-") + (control ? "n" : "-") + (inpaint ? "m" : "-") + (d->step_noise ? "z" : "-") +
                           "s" + std::to_string(S);
   const bool use_graph = d->use_cuda_graph != 0;
 
@@ -611,7 +622,7 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
     // ---- job-resident buffers (same addresses for the same configuration => the captured graph stays valid) ----
     float* latent = c.ws->alloc_n<float>((size_t)B * n);
     bf16* lat8 = c.ws->alloc_n<bf16>((size_t)Bt * h * w * 8);
-    float* eps = c.ws->alloc_n<float>((size_t)Bt * n);
+    float* eps = c.ws->alloc_n<float>((size_t)(cfg ? 2 * B : B) * n);  // [uncond B | cond B] (split: gathered from both ranks)
     float* temb_tab = c.ws->alloc_n<float>((size_t)S * 320);
     float* temb_in = c.ws->alloc_n<float>((size_t)Bt * 320);
     StepCoef* d_coefs = c.ws->alloc_n<StepCoef>(S);
@@ -643,12 +654,14 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
       // contexts -> bf16 [uncond B | cond B], K/V projections hoisted out of the step loop
       const size_t m = c.ws->mark();
       float* f = c.ws->alloc_n<float>((size_t)B * T * kCtxDim);
-      if (cfg) {
+      if (cfg && (!split || srank == 0)) {
         copy_in(f, uctx);
         c.cast_pad(f, (long long)B * T, kCtxDim, kCtxDim, 1.f, ctxb, false);
       }
-      copy_in(f, ctx);
-      c.cast_pad(f, (long long)B * T, kCtxDim, kCtxDim, 1.f, ctxb + (cfg ? (size_t)B * T * kCtxDim : 0), false);
+      if (!split || srank == 1) {
+        copy_in(f, ctx);
+        c.cast_pad(f, (long long)B * T, kCtxDim, kCtxDim, 1.f, ctxb + (dup ? (size_t)B * T * kCtxDim : 0), false);
+      }
       c.ws->release(m);
     }
     project_context(c, ctxb, Bt, T, unet_attn_layers(e->unet), kv);
@@ -659,11 +672,11 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
       float* f = c.ws->alloc_n<float>((size_t)B * H * W * 3);
       copy_in(f, hint_img);
       bf16* i8 = c.ws->alloc_n<bf16>((size_t)Bt * H * W * 8);
-      c.cast_pad(f, (long long)B * H * W, 3, 8, 1.f, i8, cfg);
+      c.cast_pad(f, (long long)B * H * W, 3, 8, 1.f, i8, dup);
       hintnet_forward(c, e->cnet, i8, Bt, H, W, hint);
       c.ws->release(m);
     }
-    c.cast_pad(latent, (long long)B * h * w, 4, 8, 1.f, lat8, cfg);
+    c.cast_pad(latent, (long long)B * h * w, 4, 8, 1.f, lat8, dup);
 
     // ---- one denoising step ----
     auto step = [&](Ctx& sc) {
@@ -677,11 +690,18 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
         controlnet_forward(sc, e->cnet, lat8, Bt, h, w, temb_in, kv_cn, hint, ctrl);
         for (int i = 0; i < 13; ++i) cptr[i] = ctrl[i].p;
       }
-      unet_forward(sc, e->unet, lat8, Bt, h, w, temb_in, kv, control ? cptr : nullptr, eps);
+      unet_forward(sc, e->unet, lat8, Bt, h, w, temb_in, kv, control ? cptr : nullptr, eps + (split ? (size_t)srank * B * n : 0));
+      if (split) {  // C1: in-place all-gather of this rank's branch; both ranks then run the update redundantly
+        ++sc.launches;
+        if (!sc.dry) {
+          NcclApi& api = nccl_api(nullptr);
+          SDTF_NCCL(api, api.AllGather(eps + (size_t)srank * B * n, eps, (size_t)B * n, kNcclFloat32, e->comm.comm, e->st));
+        }
+      }
       sc.launches += 2;
       if (!sc.dry) {
         cfg_sched_kernel<<<B, 512, 0, e->st>>>(cfg ? eps : nullptr, cfg ? eps + (size_t)B * n : eps, latent, d_coefs, e->step_dev,
-                                                d_snoise, d_mask, d_initl, d_initn, n, latent, lat8, B, cfg ? 1 : 0);
+                                                d_snoise, d_mask, d_initl, d_initn, n, latent, lat8, B, dup ? 1 : 0);
         SDTF_CUDA(cudaGetLastError());
         step_advance_kernel<<<1, 1, 0, e->st>>>(e->step_dev);
         SDTF_CUDA(cudaGetLastError());
@@ -750,6 +770,55 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
   cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->timings.decode_ms = ms;
   cudaEventElapsedTime(&ms, e->ev[0], e->ev[3]); e->timings.total_ms = ms;
   (void)t_host0;
+  SDTF_API_END
+}
+
+int sdtf_comm_unique_id(const char* nccl_lib, void* out_id128) {
+  if (!out_id128) return SDTF_ERR_INVALID;
+  try {
+    NcclApi& api = nccl_api(nccl_lib);
+    NcclUniqueId id;
+    SDTF_NCCL(api, api.GetUniqueId(&id));
+    memcpy(out_id128, &id, sizeof(id));
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return SDTF_ERR_INTERNAL;
+  }
+  return SDTF_OK;
+}
+
+int sdtf_comm_init(sdtf_engine* e, const char* nccl_lib, const void* id128, int32_t rank, int32_t world) {
+  SDTF_API_BEGIN
+  SDTF_CHECK(id128 != nullptr, "id is NULL");
+  SDTF_CHECK(world == 2 && (rank == 0 || rank == 1), "the CFG split is 2-way: world must be 2, rank 0 or 1");
+  NcclApi& api = nccl_api(nccl_lib);
+  e->drop_graph();
+  if (e->comm.comm) {
+    api.CommDestroy(e->comm.comm);
+    e->comm = Comm();
+  }
+  NcclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NcclComm c = nullptr;
+  SDTF_NCCL(api, api.CommInitRank(&c, world, id, rank));
+  e->comm.comm = c; e->comm.rank = rank; e->comm.world = world;
+  // one eager collective so that NCCL's lazy channel / buffer setup never happens under stream capture
+  float* tmp = nullptr;
+  SDTF_CUDA(cudaMalloc((void**)&tmp, sizeof(float) * 2 * 256));
+  SDTF_CUDA(cudaMemsetAsync(tmp, 0, sizeof(float) * 2 * 256, e->st));
+  SDTF_NCCL(api, api.AllGather(tmp + rank * 256, tmp, 256, kNcclFloat32, c, e->st));
+  SDTF_CUDA(cudaStreamSynchronize(e->st));
+  cudaFree(tmp);
+  SDTF_API_END
+}
+
+int sdtf_comm_destroy(sdtf_engine* e) {
+  SDTF_API_BEGIN
+  e->drop_graph();
+  if (e->comm.comm) {
+    nccl_api(nullptr).CommDestroy(e->comm.comm);
+    e->comm = Comm();
+  }
   SDTF_API_END
 }
 

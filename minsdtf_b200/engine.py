@@ -187,9 +187,30 @@ class Engine:
         self._check(self._lib.sdtf_to_uint8(self._h, dl(decoded), dl(self._f32(blend_image)), dl(self._f32(blend_mask)), dl(out)))
         return out
 
+    # ------------------------------------------------------------------------------------------------ 2-way CFG split
+    def comm_unique_id(self, nccl_lib=None) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        rc = self._lib.sdtf_comm_unique_id(nccl_lib.encode() if nccl_lib else None, buf)
+        if rc != 0:
+            msg = self._lib.sdtf_last_error(None)
+            raise EngineError(f"sdtf_comm_unique_id failed ({rc}): {msg.decode() if msg else ''}")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int = 2, nccl_lib=None):
+        """Join the 2-rank NCCL communicator of a CFG pair (rank 0 = unconditional branch, 1 = conditional)."""
+        if len(unique_id) != 128:
+            raise EngineError("NCCL unique id must be 128 bytes")
+        buf = ctypes.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.sdtf_comm_init(self._h, nccl_lib.encode() if nccl_lib else None, buf, int(rank), int(world)))
+        self.cfg_rank = int(rank)
+
+    def comm_destroy(self):
+        self._check(self._lib.sdtf_comm_destroy(self._h))
+        self.cfg_rank = None
+
     def denoise(self, latent0, context, uncond_context, t_emb, coefs, step_noise=None, mask=None, init_latent=None,
                 init_noise=None, hint_image=None, blend_image=None, blend_mask=None, decode=True, use_cuda_graph=True,
-                return_latent=False):
+                return_latent=False, cfg_split=False):
         """The whole loop of generate_image (stable_diffusion.py:442-486) in one call.  coefs: list of StepCoef in
         execution order; t_emb (n_steps, 320)."""
         latent0 = self._f32(latent0)
@@ -199,6 +220,7 @@ class Engine:
         dl = _lib.DL()
         d = _lib.DenoiseDesc()
         d.n_steps, d.use_cuda_graph, d.decode = n, int(bool(use_cuda_graph)), int(bool(decode))
+        d.cfg_split = int(bool(cfg_split))
         d.latent0 = dl(latent0)
         d.context = dl(self._f32(context))
         d.uncond_context = dl(self._f32(uncond_context))

@@ -157,7 +157,7 @@ class StableDiffusionBase:
     def generate_image(self, encoded_text, negative_prompt=None, batch_size=1, num_steps=50, unconditional_guidance_scale=7.5,
                        diffusion_noise=None, seed=None, negative_embedding=None, control_net_image=None, inpaint_mask=None,
                        mask_blur_strength=None, reference_image=None, reference_image_strength=0.8, guidance_rescale=0.0,
-                       callback=None, return_latent=False, use_cuda_graph=True):
+                       callback=None, return_latent=False, use_cuda_graph=True, cfg_split=False):
         if diffusion_noise is not None and seed is not None:
             raise ValueError("`diffusion_noise` and `seed` should not both be passed to `generate_image`. `seed` is only "
                              "used to generate diffusion noise when it's not already user-specified.")
@@ -219,7 +219,7 @@ class StableDiffusionBase:
             init_noise=noise if inpainting else None, hint_image=hint_image,
             blend_image=input_image_array[0] if blend else None,
             blend_mask=input_mask_array[0, ..., 0] if blend else None,
-            decode=True, use_cuda_graph=use_cuda_graph, return_latent=return_latent)
+            decode=True, use_cuda_graph=use_cuda_graph, return_latent=return_latent, cfg_split=cfg_split)
         if callback is not None:
             callback(len(exec_ts))
         return out
