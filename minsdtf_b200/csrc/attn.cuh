@@ -24,6 +24,8 @@ struct AttnParams {
   float scale_log2;  // d^-1/2 * log2(e)
   bf16* out;         // [B*Nq][ldo], head h at column h*d
   long long ldo;
+  long long* prof;   // optional [16] global cycle counters summed over CTAs (SDTF_ATTN_PROFILE=1), null: off
+  int debug;         // timing experiments only (SDTF_ATTN_DEBUG; results are garbage): 1 no exp, 2 no max, 4 no S load, 8 no P store, 16 no PV MMAs, 32 no QK MMAs, 64 no K/V TMA
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -238,17 +240,48 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 // d <= 64 heads (SD1.5: d = 40 at the 64x64 / 96x96 level, N = 4096 / 9216 tokens): the softmax exponentials,
 // not the tensor core, bound this shape (128 ex2 per row and tile on a 16-lane MUFU vs 384 MMA cycles), so the
 // kernel is organised around keeping the MUFU pipe busy:
-//   * one CTA owns TWO 128-row query tiles; warps 0-3 / 4-7 are the softmax groups of tile 0 / 1, warp 8 issues
-//     every tcgen05.mma, warp 9 every TMA load.  K/V tiles are fetched once for both query tiles.
+//   * one CTA owns TWO 128-row query tiles; warps 0-3 / 4-7 are the softmax groups of tile 0 / 1, warps 8 / 9 issue
+//     the tcgen05.mma of group 0 / 1 (each group is its own pipeline, so the two drift out of phase and one group's
+//     exponentials fill the MUFU while the other loads / reduces), warp 10 issues every TMA load.  K/V tiles are
+//     fetched once for both query tiles.
 //   * S_g lives in TMEM columns [128g, 128g+128).  A softmax thread pulls its whole 128-column row into
 //     registers and immediately hands the TMEM buffer back (s_empty), so Q K^T of the NEXT key tile runs while
-//     the exponentials of this one are computed; while group 0 is in its exp loop the tensor core serves group 1.
+//     the exponentials of this one are computed.
+//   * a quarter of the exponentials is evaluated on the FMA pipe (Cody-Waite split + cubic, rel. error 6e-4, below
+//     the bf16 rounding of P) instead of MUFU.EX2 (ncu: xu pipe 54 % busy, the binding unit of this kernel).
 //   * O_g accumulates in TMEM columns [256+64g, +DV) across all key tiles.  The running max is only moved (and
 //     O rescaled through tcgen05.ld/st) when it grows by more than 2^8; otherwise P is computed against the stale
 //     max (values <= 256, exact after the final division by the row sum which uses the same max).
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// 2^x on the FMA / ALU pipes: x = n + f with n = round(x) (magic-number add), 2^f by a cubic on [-0.5, 0.5],
+// 2^n by an integer add into the exponent field.  Valid for x in [-126, 126].
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;  // 1.5 * 2^23: the low mantissa bits of t hold n
+  const float f = x - (t - 12582912.f);
+  const float p = fmaf(fmaf(fmaf(0.0555041f, f, 0.2402265f), f, 0.6931472f), f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+static constexpr int kA2Threads = 352;
+#define A2_TIMED(acc, stmt)                    \
+  do {                                         \
+    if (prof_on) {                             \
+      const long long _t0 = clock64();         \
+      stmt;                                    \
+      acc += clock64() - _t0;                  \
+    } else {                                   \
+      stmt;                                    \
+    }                                          \
+  } while (0)
+
 template <int KS, int DV>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(kA2Threads, 1)
 attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using namespace tc05;
@@ -280,15 +313,17 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
   const int col0 = head * p.dstride;
   const int nkv = (p.Nk + 127) / 128;
+  const bool prof_on = p.prof != nullptr;
+  const long long t_start = prof_on ? clock64() : 0;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
-    for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1); }
-    for (int s = 0; s < VST; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1); }
+    for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 2); }  // released by both groups' MMA warps
+    for (int s = 0; s < VST; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 2); }
     for (int g = 0; g < 2; ++g) {
-      mbar_init(s_full(g), 1); mbar_init(s_empty(g), 4);  // one arrive per softmax warp (128 per-thread arrives on one
-      mbar_init(p_full(g), 4); mbar_init(o_done(g), 1);   // barrier serialise as shared-memory atomics)
+      mbar_init(s_full(g), 1); mbar_init(s_empty(g), 4);  // one arrive per softmax warp
+      mbar_init(p_full(g), 4); mbar_init(o_done(g), 1);
     }
     fence_mbar_init();
   }
@@ -304,67 +339,85 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     return (n + 15) & ~15;
   };
 
-  if (warp == 9) {
+  if (warp == 10) {
     // ===== TMA producer =====
     if (elect_one()) {
       mbar_expect_tx(q_full, 2 * kChunk);
       tma_load_3d(sQ, &tmQ, q_full, col0, q0, b);
       tma_load_3d(sQ + kChunk, &tmQ, q_full, col0, q0 + 128, b);
+      long long w_ke = 0, w_ve = 0;
       for (int j = 0; j < nkv; ++j) {
         const int ks = j % KST, vs = j % VST;
-        mbar_wait(k_empty(ks), ((uint32_t)(j / KST) & 1u) ^ 1u);
-        mbar_expect_tx(k_full(ks), kChunk);
-        tma_load_3d(sK + ks * kChunk, &tmK, k_full(ks), col0, j * 128, b);
-        mbar_wait(v_empty(vs), ((uint32_t)(j / VST) & 1u) ^ 1u);
-        mbar_expect_tx(v_full(vs), kChunk);
-        tma_load_3d(sV + vs * kChunk, &tmV, v_full(vs), col0, j * 128, b);
+        A2_TIMED(w_ke, mbar_wait(k_empty(ks), ((uint32_t)(j / KST) & 1u) ^ 1u));
+        if (p.debug & 64) mbar_arrive(k_full(ks));
+        else {
+          mbar_expect_tx(k_full(ks), kChunk);
+          tma_load_3d(sK + ks * kChunk, &tmK, k_full(ks), col0, j * 128, b);
+        }
+        A2_TIMED(w_ve, mbar_wait(v_empty(vs), ((uint32_t)(j / VST) & 1u) ^ 1u));
+        if (p.debug & 64) mbar_arrive(v_full(vs));
+        else {
+          mbar_expect_tx(v_full(vs), kChunk);
+          tma_load_3d(sV + vs * kChunk, &tmV, v_full(vs), col0, j * 128, b);
+        }
+      }
+      if (prof_on) {
+        atomicAdd((unsigned long long*)p.prof + 0, (unsigned long long)w_ke);
+        atomicAdd((unsigned long long*)p.prof + 1, (unsigned long long)w_ve);
+        atomicAdd((unsigned long long*)p.prof + 2, (unsigned long long)(clock64() - t_start));
       }
     }
     __syncwarp();
-  } else if (warp == 8) {
-    // ===== MMA issuer =====
+  } else if (warp == 8 || warp == 9) {
+    // ===== MMA issuer of group g = warp - 8 =====
     if (elect_one()) {
-      auto issue_qk = [&](int g, int j) {
+      const int g = warp - 8;
+      const uint32_t tS = tmem + 128u * g, tO = tmem + 256u + 64u * g;
+      const uint64_t dq = make_smem_desc_sw128(sQ + g * kChunk, 16, 1024);
+      const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * g) * kChunk, 16, 1024);
+      auto issue_qk = [&](int j) {
         const int st = j % KST;
         const uint32_t idesc = make_idesc_bf16(128, keys_in_tile(j), 0, 0);
+        const uint64_t dk = make_smem_desc_sw128(sK + st * kChunk, 16, 1024);
+        if (!(p.debug & 32)) {
 #pragma unroll
-        for (int k = 0; k < KS; ++k)
-          mma_f16_ss(tmem + 128u * g, make_smem_desc_sw128(sQ + g * kChunk + k * 32u, 16, 1024),
-                     make_smem_desc_sw128(sK + st * kChunk + k * 32u, 16, 1024), idesc, k != 0);
+          for (int k = 0; k < KS; ++k) mma_f16_ss(tS, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+        }
         mma_commit(s_full(g));
+        mma_commit(k_empty(st));
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full(0), 0);
+      long long w_kf = 0, w_se = 0, w_vf = 0, w_pf = 0;
+      A2_TIMED(w_kf, mbar_wait(q_full, 0));
+      A2_TIMED(w_kf, mbar_wait(k_full(0), 0));
       fence_after_sync();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      mma_commit(k_empty(0));
+      issue_qk(0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) {
-          const int st = (j + 1) % KST;
-          mbar_wait(k_full(st), (uint32_t)((j + 1) / KST) & 1u);
-          for (int g = 0; g < 2; ++g) {
-            mbar_wait(s_empty(g), (uint32_t)j & 1u);  // S_j(g) has been pulled into registers
-            fence_after_sync();
-            issue_qk(g, j + 1);
-          }
-          mma_commit(k_empty(st));
+          A2_TIMED(w_kf, mbar_wait(k_full((j + 1) % KST), (uint32_t)((j + 1) / KST) & 1u));
+          A2_TIMED(w_se, mbar_wait(s_empty(g), (uint32_t)j & 1u));  // S_j has been pulled into registers
+          fence_after_sync();
+          issue_qk(j + 1);
         }
         const int vs = j % VST;
-        mbar_wait(v_full(vs), (uint32_t)(j / VST) & 1u);
-        const uint32_t idesc = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
+        A2_TIMED(w_vf, mbar_wait(v_full(vs), (uint32_t)(j / VST) & 1u));
+        A2_TIMED(w_pf, mbar_wait(p_full(g), (uint32_t)j & 1u));  // P_j is in shared memory
+        fence_after_sync();
         const int ksteps = keys_in_tile(j) >> 4;
-        for (int g = 0; g < 2; ++g) {
-          mbar_wait(p_full(g), (uint32_t)j & 1u);  // P_j(g) is in shared memory
-          fence_after_sync();
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t da = make_smem_desc_sw128(sP + (uint32_t)(2 * g + (k >> 2)) * kChunk + (uint32_t)(k & 3) * 32u, 16, 1024);
-            const uint64_t db = make_smem_desc_sw128(sV + vs * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
-            mma_f16_ss(tmem + 256u + 64u * g, da, db, idesc, (j | k) != 0);
-          }
-          mma_commit(o_done(g));
+        for (int k = 0; k < ksteps && !(p.debug & 16); ++k) {
+          const uint64_t da = dp + (uint64_t)((k >> 2) * (kChunk >> 4) + (k & 3) * 2);
+          const uint64_t db = make_smem_desc_sw128(sV + vs * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
+          mma_f16_ss(tO, da, db, idesc_pv, (j | k) != 0);
         }
+        mma_commit(o_done(g));
         mma_commit(v_empty(vs));
+      }
+      if (prof_on && g == 0) {
+        atomicAdd((unsigned long long*)p.prof + 3, (unsigned long long)w_kf);
+        atomicAdd((unsigned long long*)p.prof + 4, (unsigned long long)w_se);
+        atomicAdd((unsigned long long*)p.prof + 5, (unsigned long long)w_vf);
+        atomicAdd((unsigned long long*)p.prof + 6, (unsigned long long)w_pf);
+        atomicAdd((unsigned long long*)p.prof + 7, (unsigned long long)(clock64() - t_start));
       }
     }
     __syncwarp();
@@ -378,16 +431,22 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     uint8_t* rowp = gen + (sP - base) + (uint32_t)(2 * g) * kChunk + row * 128;
     const int sw = row & 7;
     float m_run = -INFINITY, l_run = 0.f;
+    long long w_sf = 0, w_od = 0, t_loop = 0;
     for (int j = 0; j < nkv; ++j) {
       const int nk_valid = min(128, p.Nk - j * 128);
-      mbar_wait(s_full(g), (uint32_t)j & 1u);
+      A2_TIMED(w_sf, mbar_wait(s_full(g), (uint32_t)j & 1u));
       fence_after_sync();
       uint32_t sv[128];
-      tmem_ld32_at<0>(tS, sv);
-      tmem_ld32_at<32>(tS + 32, sv);
-      tmem_ld32_at<64>(tS + 64, sv);
-      tmem_ld32_at<96>(tS + 96, sv);
-      tmem_ld_wait();
+      if (!(p.debug & 4)) {
+        tmem_ld32_at<0>(tS, sv);
+        tmem_ld32_at<32>(tS + 32, sv);
+        tmem_ld32_at<64>(tS + 64, sv);
+        tmem_ld32_at<96>(tS + 96, sv);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 128; ++i) sv[i] = __float_as_uint(0.001f * (float)(i + lane));
+      }
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty(g));
@@ -396,16 +455,22 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         for (int i = 0; i < 128; ++i)
           if (i >= nk_valid) sv[i] = 0xff800000u;  // -inf
       }
-      float mx = __uint_as_float(sv[0]);
+      float mx = fmax3(__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]));
+      float mx2 = fmax3(__uint_as_float(sv[3]), __uint_as_float(sv[4]), __uint_as_float(sv[5]));
 #pragma unroll
-      for (int i = 1; i + 1 < 128; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])));
-      mx = fmaxf(mx, __uint_as_float(sv[127]));
+      for (int i = 6; i + 3 < 128; i += 4) {
+        mx = fmax3(mx, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        mx2 = fmax3(mx2, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+      }
+      mx = fmax3(mx, mx2, fmaxf(__uint_as_float(sv[126]), __uint_as_float(sv[127])));
+      if (p.debug & 2) mx = __uint_as_float(sv[5]);
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const bool grow = (m_new - m_run) > 8.f;
       if (j > 0) {  // PV_{j-1}(g) must be complete before O is touched or P overwritten
-        mbar_wait(o_done(g), (uint32_t)(j - 1) & 1u);
+        A2_TIMED(w_od, mbar_wait(o_done(g), (uint32_t)(j - 1) & 1u));
         fence_after_sync();
       }
+      const long long t_l0 = prof_on ? clock64() : 0;
       if (__any_sync(0xffffffffu, grow)) {
         const float alpha = ex2f(m_run - m_new);
         m_run = m_new;
@@ -429,20 +494,31 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int c = 0; c < 128; c += 8) {
         float e[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) e[i] = ex2f(fmaf(__uint_as_float(sv[c + i]), p.scale_log2, neg_m));
+        for (int i = 0; i < 8; ++i) {
+          const float xarg = fmaf(__uint_as_float(sv[c + i]), p.scale_log2, neg_m);
+          e[i] = (i >= 6) ? ex2_poly(xarg) : ex2f(xarg);  // 2 of 8 on the FMA pipe
+          if (p.debug & 1) e[i] = xarg;
+        }
         lsum0 += (e[0] + e[1]) + (e[2] + e[3]);
         lsum1 += (e[4] + e[5]) + (e[6] + e[7]);
         uint4 w;
         w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]);
         w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
         const int chunk = c >> 6, u = (c & 63) >> 3;
-        *reinterpret_cast<uint4*>(rowp + chunk * kChunk + ((u ^ sw) << 4)) = w;
+        if (!(p.debug & 8)) *reinterpret_cast<uint4*>(rowp + chunk * kChunk + ((u ^ sw) << 4)) = w;
       }
       l_run += lsum0 + lsum1;
       fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(g));
+      if (prof_on) t_loop += clock64() - t_l0;
+    }
+    if (prof_on && threadIdx.x == 0) {
+      atomicAdd((unsigned long long*)p.prof + 8, (unsigned long long)w_sf);
+      atomicAdd((unsigned long long*)p.prof + 9, (unsigned long long)w_od);
+      atomicAdd((unsigned long long*)p.prof + 10, (unsigned long long)t_loop);
+      atomicAdd((unsigned long long*)p.prof + 11, (unsigned long long)(clock64() - t_start));
     }
     // ---- epilogue: O / l -> bf16 ----
     mbar_wait(o_done(g), (uint32_t)(nkv - 1) & 1u);
@@ -475,7 +551,309 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   fence_before_sync();
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, kTmemCols);
+  if (prof_on && threadIdx.x == 0) atomicAdd((unsigned long long*)p.prof + 12, (unsigned long long)(clock64() - t_start));
 }
+
+// ------------------------------------------------------------------------------------------------------
+// attn2h: the d <= 64 kernel with HALF-ROW softmax threads.  Profiling attn2q (one thread per 128-wide S row) showed
+// the softmax warps, not MUFU / tensor / barriers, bound it: ~850 instructions per warp and key tile at IPC 0.38 —
+// two warps per scheduler holding 128 live S registers each cannot hide their own latencies.  Here a query row is
+// served by TWO threads (keys [0,64) and [64,128) of every key tile), 16 softmax warps in all: four warps per
+// scheduler, half the live registers, and the halves never have to agree on a maximum because each keeps its own
+// online-softmax state (m, l) and its own accumulator O_{g,h} in TMEM (4 x 48 columns); P V for a half starts as soon
+// as that half's 64 columns of P are in shared memory.  The two partial results are merged once, at the end:
+// O = (O_a 2^(m_a-m) + O_b 2^(m_b-m)) / (l_a 2^(m_a-m) + l_b 2^(m_b-m)).
+// Warps 0-15 softmax (quad = w&3, query tile g = (w>>2)&1, half h = w>>3), 16/17 MMA issue of tile 0/1, 18 TMA.
+// ------------------------------------------------------------------------------------------------------
+static constexpr int kAHThreads = 640;  // 16 softmax warps + one control warpgroup (MMA x2, TMA, idle)
+template <int N>
+__device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 2, 512;" ::: "memory"); }
+
+template <int KS, int DV>
+__global__ void __launch_bounds__(kAHThreads, 1)
+attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using namespace tc05;
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kChunk = 128 * 128;  // [128 rows][64 bf16] swizzled = 16 KB
+  constexpr int KST = 3, VST = 3;
+  constexpr uint32_t kTmemCols = 512;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;                       // 2 chunks
+  const uint32_t sK = sQ + 2 * kChunk;            // KST chunks
+  const uint32_t sV = sK + KST * kChunk;          // VST chunks
+  const uint32_t sP = sV + VST * kChunk;          // chunk 2g+h = P of query tile g, key half h
+  const uint32_t xch_off = (sP - base) + 4 * kChunk;  // float2 [256]: (m, l) of the h = 1 threads for the final merge
+  const uint32_t bars = base + xch_off + 2048u;
+  const uint32_t q_full = bars;
+  auto k_full = [&](int s) { return bars + 8u + 8u * s; };
+  auto k_empty = [&](int s) { return bars + 8u + 8u * (KST + s); };
+  auto v_full = [&](int s) { return bars + 8u + 8u * (2 * KST + s); };
+  auto v_empty = [&](int s) { return bars + 8u + 8u * (2 * KST + VST + s); };
+  const uint32_t gbars = bars + 8u + 8u * (2 * KST + 2 * VST);
+  auto s_full = [&](int g) { return gbars + 8u * g; };
+  auto s_empty = [&](int g) { return gbars + 16u + 8u * g; };
+  auto p_full = [&](int g, int h) { return gbars + 32u + 8u * (2 * g + h); };
+  auto o_done = [&](int g, int h) { return gbars + 64u + 8u * (2 * g + h); };
+  auto v_ones = [&](int s) { return gbars + 96u + 8u * s; };
+  const uint32_t tmem_slot = gbars + 96u + 8u * VST;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
+  const int col0 = head * p.dstride;
+  const int nkv = (p.Nk + 127) / 128;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 2); }  // released by both tiles' MMA warps
+    for (int s = 0; s < VST; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 2); mbar_init(v_ones(s), 1); }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full(g), 1);
+      mbar_init(s_empty(g), 8);  // one arrive per softmax warp of the tile (both halves)
+      for (int h = 0; h < 2; ++h) { mbar_init(p_full(g, h), 4); mbar_init(o_done(g, h), 1); }
+    }
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  auto keys_in_tile = [&](int j) {  // valid keys of tile j rounded up to the MMA granularity
+    int n = p.Nk - j * 128;
+    n = n > 128 ? 128 : n;
+    return (n + 15) & ~15;
+  };
+
+  // register budget: the kernel is compiled for 96 registers per thread (640 x 96 = 60 K); the control warpgroup hands
+  // most of its share back so that the softmax warpgroups can hold a 64-wide S row without spilling
+  // (setmaxnreg: ptxas refuses to allocate this kernel under a per-warpgroup budget)
+
+  if (warp == 18) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * kChunk);
+      tma_load_3d(sQ, &tmQ, q_full, col0, q0, b);
+      tma_load_3d(sQ + kChunk, &tmQ, q_full, col0, q0 + 128, b);
+      for (int j = 0; j < nkv; ++j) {
+        const int ks = j % KST, vs = j % VST;
+        mbar_wait(k_empty(ks), ((uint32_t)(j / KST) & 1u) ^ 1u);
+        mbar_expect_tx(k_full(ks), kChunk);
+        tma_load_3d(sK + ks * kChunk, &tmK, k_full(ks), col0, j * 128, b);
+        mbar_wait(v_empty(vs), ((uint32_t)(j / VST) & 1u) ^ 1u);
+        mbar_expect_tx(v_full(vs), kChunk);
+        tma_load_3d(sV + vs * kChunk, &tmV, v_full(vs), col0, j * 128, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 16 || warp == 17) {
+    // ===== MMA issuer of query tile g = warp - 16 =====
+    if (elect_one()) {
+      const int g = warp - 16;
+      const uint32_t tS = tmem + 128u * g;
+      const uint64_t dq = make_smem_desc_sw128(sQ + g * kChunk, 16, 1024);
+      auto issue_qk = [&](int j) {
+        const int st = j % KST;
+        const uint32_t idesc = make_idesc_bf16(128, keys_in_tile(j), 0, 0);
+        const uint64_t dk = make_smem_desc_sw128(sK + st * kChunk, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) mma_f16_ss(tS, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+        mma_commit(s_full(g));
+        mma_commit(k_empty(st));
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full(0), 0);
+      fence_after_sync();
+      issue_qk(0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) {
+          mbar_wait(k_full((j + 1) % KST), (uint32_t)((j + 1) / KST) & 1u);
+          mbar_wait(s_empty(g), (uint32_t)j & 1u);  // both halves of S_j are in registers
+          fence_after_sync();
+          issue_qk(j + 1);
+        }
+        const int vs = j % VST;
+        mbar_wait(v_ones(vs), (uint32_t)(j / VST) & 1u);  // V tile landed and its ones column is in place
+        fence_after_sync();
+        const int ksteps = keys_in_tile(j) >> 4;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(p_full(g, h), (uint32_t)j & 1u);  // this half of P_j is in shared memory
+          fence_after_sync();
+          const uint32_t tO = tmem + 256u + (uint32_t)(DV * (2 * g + h));
+          const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * g + h) * kChunk, 16, 1024);
+          for (int k = 4 * h; k < 4 * h + 4 && k < ksteps; ++k) {
+            const uint64_t db = make_smem_desc_sw128(sV + vs * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
+            mma_f16_ss(tO, dp + 2 * (k & 3), db, idesc_pv, (j > 0) || (k > 4 * h));
+          }
+          mma_commit(o_done(g, h));
+        }
+        mma_commit(v_empty(vs));
+      }
+    }
+    __syncwarp();
+  } else if (warp == 19) {
+    // ===== ones column: V[:, d] = 1 in every landed V tile, so that P V also produces the softmax denominator
+    // (column d of O = sum_k P[q,k]) on the tensor core instead of one FADD per exponential in the softmax warps
+    const uint32_t chunk = (uint32_t)(p.d * 2) >> 4, within = (uint32_t)(p.d * 2) & 15u;
+    for (int j = 0; j < nkv; ++j) {
+      const int vs = j % VST;
+      mbar_wait(v_full(vs), (uint32_t)(j / VST) & 1u);
+      uint8_t* vt = gen + (sV - base) + (uint32_t)vs * kChunk;
+#pragma unroll
+      for (int r = lane; r < 128; r += 32)
+        *reinterpret_cast<uint16_t*>(vt + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4) + within) = 0x3F80;  // bf16 1.0
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_ones(vs));
+    }
+  } else if (warp < 16) {
+    // ===== softmax: thread = (query row, key half) =====
+    const int g = (warp >> 2) & 1, h = warp >> 3;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + 128u * g + 64u * h + lane_off;
+    const uint32_t tO = tmem + 256u + (uint32_t)(DV * (2 * g + h)) + lane_off;
+    uint8_t* rowp = gen + (sP - base) + (uint32_t)(2 * g + h) * kChunk + row * 128;
+    const int sw = row & 7;
+    float m_run = -INFINITY;  // (the running denominator lives in column d of the accumulator)
+    for (int j = 0; j < nkv; ++j) {
+      int nvalid = p.Nk - j * 128 - 64 * h;  // valid keys of this half
+      nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
+      mbar_wait(s_full(g), (uint32_t)j & 1u);
+      fence_after_sync();
+      uint32_t sv[64];
+      tmem_ld32_at<0>(tS, sv);
+      tmem_ld32_at<32>(tS + 32, sv);
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty(g));
+      if (nvalid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= nvalid) sv[i] = 0xff800000u;  // -inf
+      }
+      float mx = fmax3(__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]));
+      float mx2 = fmax3(__uint_as_float(sv[3]), __uint_as_float(sv[4]), __uint_as_float(sv[5]));
+#pragma unroll
+      for (int i = 6; i + 3 < 64; i += 4) {
+        mx = fmax3(mx, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        mx2 = fmax3(mx2, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+      }
+      mx = fmax3(mx, mx2, fmaxf(__uint_as_float(sv[62]), __uint_as_float(sv[63])));
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const bool grow = (m_new - m_run) > 8.f;  // (-inf) - (-inf) = NaN -> false: nothing to move
+      if (j > 0) {  // P V_{j-1} of this half must be complete before O is touched or P overwritten
+        mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+        fence_after_sync();
+      }
+      if (__any_sync(0xffffffffu, grow)) {
+        const float alpha = grow ? ex2f(m_run - m_new) : 1.f;
+        if (grow) m_run = m_new;
+        if (j > 0) {
+#pragma unroll
+          for (int c = 0; c < DV; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(tO + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(tO + c, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;  // no valid key yet: every term below becomes 2^-inf = 0
+#pragma unroll
+      for (int c = 0; c < 64; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float xarg = fmaf(__uint_as_float(sv[c + i]), p.scale_log2, neg_m);
+          e[i] = (i >= 6) ? ex2_poly(xarg) : ex2f(xarg);  // 2 of 8 on the FMA pipe
+        }
+        // (masked keys were set to -inf above: 2^-inf = 0 on the MUFU path, 2^-126 on the FMA path — below anything bf16 keeps)
+        uint4 w;
+        w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]);
+        w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
+        *reinterpret_cast<uint4*>(rowp + (((c >> 3) ^ sw) << 4)) = w;
+      }
+      fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(g, h));
+    }
+    // ---- merge the two halves of each row and write O / l as bf16 ----
+    float2* xch = reinterpret_cast<float2*>(gen + xch_off);
+    if (h == 1) xch[g * 128 + row] = make_float2(m_run, 0.f);
+    softmax_bar_sync();
+    if (h == 0) {
+      mbar_wait(o_done(g, 0), (uint32_t)(nkv - 1) & 1u);
+      mbar_wait(o_done(g, 1), (uint32_t)(nkv - 1) & 1u);
+      fence_after_sync();
+      const float2 other = xch[g * 128 + row];
+      const float m_all = fmaxf(m_run, other.x);
+      const float fa = (m_run == -INFINITY) ? 0.f : ex2f(m_run - m_all);
+      const float fb = (other.x == -INFINITY) ? 0.f : ex2f(other.x - m_all);
+      const uint32_t tOb = tO + (uint32_t)DV;  // accumulator of the other half (same TMEM lanes)
+      float la, lb;  // denominators: column d of each accumulator
+      {
+        uint32_t va[16], vb[16];
+        const int cl = p.d & ~15;
+        tmem_ld16(tO + cl, va);
+        tmem_ld16(tOb + cl, vb);
+        tmem_ld_wait();
+        la = 0.f; lb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i == (p.d & 15)) { la = __uint_as_float(va[i]); lb = __uint_as_float(vb[i]); }
+      }
+      const float inv_l = 1.f / ((fa != 0.f ? la * fa : 0.f) + (fb != 0.f ? lb * fb : 0.f));
+      const float ca = fa * inv_l, cb = fb * inv_l;
+      const int q = q0 + g * 128 + row;
+      const bool ok = q < p.Nq;
+      bf16* orow = p.out + ((long long)b * p.Nq + q) * p.ldo + head * p.d;
+#pragma unroll
+      for (int c = 0; c < DV; c += 16) {
+        uint32_t va[16], vb[16];
+        tmem_ld16(tO + c, va);
+        tmem_ld16(tOb + c, vb);
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float xa = fa != 0.f ? __uint_as_float(va[i]) : 0.f;  // an accumulator that never saw a key is uninitialised
+          const float xb = fb != 0.f ? __uint_as_float(vb[i]) : 0.f;
+          o[i] = xa * ca + xb * cb;
+        }
+        if (ok) {
+          uint4 w0, w1;
+          w0.x = pack_bf16(o[0], o[1]);   w0.y = pack_bf16(o[2], o[3]);
+          w0.z = pack_bf16(o[4], o[5]);   w0.w = pack_bf16(o[6], o[7]);
+          w1.x = pack_bf16(o[8], o[9]);   w1.y = pack_bf16(o[10], o[11]);
+          w1.z = pack_bf16(o[12], o[13]); w1.w = pack_bf16(o[14], o[15]);
+          if (c + 8 <= p.d) *reinterpret_cast<uint4*>(orow + c) = w0;
+          if (c + 16 <= p.d) *reinterpret_cast<uint4*>(orow + c + 8) = w1;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem, kTmemCols);
+}
+
+constexpr size_t attn2h_smem_bytes() { return 1024 + (size_t)(2 + 3 + 3 + 4) * 128 * 128 + 2048 + 8 + 8 * 12 + 96 + 8 * 3 + 16 + 16; }
 
 constexpr size_t attn2q_smem_bytes() { return 1024 + (size_t)(2 + 3 + 3 + 4) * 128 * 128 + 8 + 8 * 12 + 64 + 16; }
 
@@ -511,6 +889,7 @@ inline void init_attn_t() {
 inline void init_attn_kernels() {
   init_attn_t<1, 3, 48, 2, 2>();
   SDTF_CUDA(cudaFuncSetAttribute(attn2q_kernel<3, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2q_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
   init_attn_t<2, 5, 80, 2, 2>();
   init_attn_t<3, 10, 160, 1, 1>();
 }
@@ -530,6 +909,16 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
   p.Nq = a.Nq; p.Nk = a.Nk; p.d = a.d; p.dstride = a.dstride;
   p.scale_log2 = (float)(1.4426950408889634 / sqrt((double)a.d));
   p.out = a.out; p.ldo = a.ldo;
+  static const int attn_debug = getenv("SDTF_ATTN_DEBUG") ? atoi(getenv("SDTF_ATTN_DEBUG")) : 0;
+  p.debug = attn_debug;
+  static const int attn_profile = getenv("SDTF_ATTN_PROFILE") ? atoi(getenv("SDTF_ATTN_PROFILE")) : 0;
+  static long long* prof_buf = nullptr;
+  p.prof = nullptr;
+  if (attn_profile && a.d == 40 && !a.legacy) {
+    if (!prof_buf) SDTF_CUDA(cudaMalloc((void**)&prof_buf, 16 * sizeof(long long)));
+    SDTF_CUDA(cudaMemsetAsync(prof_buf, 0, 16 * sizeof(long long), stream));
+    p.prof = prof_buf;
+  }
   const int cols = a.heads * a.dstride;
   CUtensorMap tq = make_tok_tmap(a.q, cols, a.Nq, a.B, a.ldq);
   CUtensorMap tk = make_tok_tmap(a.k, cols, a.Nk, a.B, a.ldk);
@@ -540,8 +929,26 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
       launch_attn_t<1, 3, 48, 2, 2>(stream, a, p, tq, tk, tv);
     } else {
       dim3 grid((unsigned)ceil_div(a.Nq, 256), (unsigned)a.heads, (unsigned)a.B);
-      attn2q_kernel<3, 48><<<grid, 320, attn2q_smem_bytes(), stream>>>(tq, tk, tv, p);
+      static const int use_2q = getenv("SDTF_ATTN_2Q") ? atoi(getenv("SDTF_ATTN_2Q")) : 0;  // A/B: previous full-row kernel
+      if (!use_2q) {
+        SDTF_CHECK(a.d < 48, "attn2h keeps the softmax denominator in accumulator column d: needs d < DV");
+        attn2h_kernel<3, 48><<<grid, kAHThreads, attn2h_smem_bytes(), stream>>>(tq, tk, tv, p);
+        SDTF_CUDA(cudaGetLastError());
+        return;
+      }
+      attn2q_kernel<3, 48><<<grid, kA2Threads, attn2q_smem_bytes(), stream>>>(tq, tk, tv, p);
       SDTF_CUDA(cudaGetLastError());
+      if (p.prof) {  // debug: per-role wait cycles, averaged per CTA
+        SDTF_CUDA(cudaStreamSynchronize(stream));
+        long long h[16];
+        SDTF_CUDA(cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost));
+        const double n = (double)grid.x * grid.y * grid.z;
+        fprintf(stderr,
+                "[attn2q-prof] per CTA: tma wait k_empty %.0f v_empty %.0f / %.0f | mma(g0) wait k_full %.0f s_empty %.0f v_full %.0f p_full "
+                "%.0f / %.0f | softmax(w0) wait s_full %.0f o_done %.0f loop-body %.0f / %.0f | cta total %.0f (nkv %d)\n",
+                h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, h[7] / n, h[8] / n, h[9] / n, h[10] / n, h[11] / n,
+                h[12] / n, (a.Nk + 127) / 128);
+      }
     }
   } else if (a.d == 80) {
     SDTF_CHECK(a.dstride == 80, "d=80 heads are stored densely");

@@ -28,7 +28,7 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ float gelu_tanh_fast(float g) {
   const float u = g * 0.7978845608f * (1.f + 0.044715f * g * g);
   return 0.5f * g * (1.f + tanh_approx(u));
@@ -41,6 +41,7 @@ struct Gemm3Extra {
   int n_mma;             // MMA instructions along N per k-step (BN / n_mma columns each, <= 256)
   int ncols;             // output columns per tile (BN, or BN/2 for GEGLU)
   int log_rows_per_b;    // log2(bw*bh): tile row >> this = sample offset inside the tile
+  int nbufs;             // staging buffers in use (<= kG3MaxBufs)
   int vec_rows;          // rows of the per-tile epilogue vector staged in smem: samples a tile spans (time-embedding conv) or 1
   int vec_width;         // its width in floats (tile columns, rounded up to 32)
   long long* prof;       // optional [gridDim.x][16] cycle counters per role (null: off); see gemm_host.cuh
@@ -59,8 +60,8 @@ struct Gemm3Extra {
     }                                           \
   } while (0)
 
-static constexpr int kG3Threads = 224;
-static constexpr int kG3Bufs = 4;                 // staging buffers
+static constexpr int kG3Threads = 384;
+static constexpr int kG3MaxBufs = 8;              // staging buffers: x.nbufs of them (4, or 8 when residual tiles must be prefetched deep)
 static constexpr uint32_t kG3BufBytes = 128 * 64; // 128 rows x 32 bf16
 
 template <int CG>
@@ -75,7 +76,9 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t b_rows = (uint32_t)p.BN / CG;  // weight rows this CTA loads per stage
   const uint32_t stage_bytes = kATileBytes + b_rows * 128u;
   const uint32_t stg_off = (uint32_t)p.stages * stage_bytes;
-  const uint32_t bar_off = stg_off + kG3Bufs * kG3BufBytes;
+  const int kG3Bufs = x.nbufs;  // 4 or 8
+  const int nb_mask = kG3Bufs - 1, nb_shift = kG3Bufs == 8 ? 3 : 2;
+  const uint32_t bar_off = stg_off + (uint32_t)kG3Bufs * kG3BufBytes;
   const uint32_t bar_base = smem_base + bar_off;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (p.stages + s); };
@@ -112,7 +115,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4 * CG);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(a), 8 * CG);  // one arrive per epilogue warp
     }
     for (int b = 0; b < kG3Bufs; ++b) {
       mbar_init(res_bar(b), 1);
@@ -237,7 +240,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (prof_on) { prof[2] = w_full; prof[3] = w_tempty; prof[4] = clock64() - t_start; }
     }
     __syncwarp();
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     // ===== store warp: TMA stores of staged sub-tiles; grants staging buffers (with the residual tile when there is one)
     if (elect_one()) {
       const bool geglu = (p.act == ACT_GEGLU);
@@ -248,11 +251,11 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       (void)geglu;
       const int my_units = unit0 < total_units ? (total_units - unit0 + unit_step - 1) / unit_step : 0;
       const int total_passes = my_units * passes;
-      // grant cursor: pass gg = (unit gu, pass gps) may use buffer gg % kG3Bufs
+      // grant cursor: pass gg = (unit gu, pass gps) may use buffer gg & nb_mask
       int gu = unit0, gps = 0, gg = 0;
       auto grant = [&]() {
         if (gg >= total_passes) return;
-        const int buf = gg % kG3Bufs;
+        const int buf = gg & nb_mask;
         if (has_res) {
           int n_tile, x0, y0, b0;
           tile_coords(gu, n_tile, x0, y0, b0);
@@ -272,9 +275,9 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         int n_tile, x0, y0, b0;
         tile_coords(u, n_tile, x0, y0, b0);
         for (int ps = 0; ps < passes; ++ps, ++sg) {
-          const int buf = sg % kG3Bufs;
+          const int buf = sg & nb_mask;
           // all 4 epilogue warps staged (and fenced) their rows
-          G3_TIMED(prof_on, w_stg, mbar_wait(stg_bar(buf), (uint32_t)(sg / kG3Bufs) & 1u));
+          G3_TIMED(prof_on, w_stg, mbar_wait(stg_bar(buf), (uint32_t)(sg >> nb_shift) & 1u));
           tma_store_4d(&tmOut, smem_base + stg_off + (uint32_t)buf * kG3BufBytes, n_tile * ncols + pass_col(ps), x0, y0, b0);
           bulk_commit();
           if (sg >= 1) {
@@ -288,9 +291,11 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (prof_on) { prof[5] = w_stg; prof[6] = w_read; prof[7] = clock64() - t_start; }
     }
     __syncwarp();
-  } else {
-    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4 =====
+  } else if (warp >= 4) {
+    // ===== epilogue warps 4..11: two sets of four (set = passes of even / odd global index), TMEM lane quadrant = warp % 4.
+    // Two epilogue warps per SM sub-partition hide each other's TMEM-load / shared-memory / MUFU latencies.
     const int quad = warp & 3;
+    const int set = (warp - 4) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
     const bool geglu = (p.act == ACT_GEGLU);
@@ -302,24 +307,27 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     auto pass_col = [&](int ps) { return (ps * 32 + 32 <= ncols || ncols < 32) ? ps * 32 : ncols - 32; };
 
     long long w_tfull = 0, w_grant = 0;
-    const int et = (int)threadIdx.x - 64;  // 0..127
+    const int et = (int)threadIdx.x - 128;  // 0..255 (set 0: 0..127)
     const bool has_vec = p.bias != nullptr || p.temb != nullptr;
     const int vrows = x.vec_rows, vwidth = x.vec_width;
     const int Nvec = geglu ? p.N : Nout;
     float* vec = reinterpret_cast<float*>(smem_gen + vec_off);
-    int lt = 0, g = 0;
+    int lt = 0;
     for (int u = unit0; u < total_units; u += unit_step, ++lt) {
       int n_tile, x0, y0, b0;
       tile_coords(u, n_tile, x0, y0, b0);
       const int acc = lt % x.acc_bufs;
       const uint32_t t_row = tmem_base + (uint32_t)(acc * x.acc_stride) + lane_off;
+      const int g0 = lt * passes;                       // global index of this tile's pass 0
+      const int ps0 = (g0 ^ set) & 1;                   // first pass of this tile that belongs to this set
+      const int ps_last = ps0 + ((passes - 1 - ps0) & ~1);  // last one (< ps0 if the set has none)
       int vr = row >> x.log_rows_per_b;  // sample of this row inside the tile
       vr = vr < vrows ? vr : vrows - 1;
       // this tile's per-column vector (bias, + the time-embedding row of each sample the tile spans): fetched from
       // global BEFORE waiting for the accumulator so the latency hides behind the main loop, then staged in smem
       float4 pre[4];
       const int vcol = 4 * et;
-      if (has_vec && vcol < vwidth) {
+      if (has_vec && et < 128 && vcol < vwidth) {
         const int gcol = n_tile * (geglu ? p.BN : ncols) + vcol;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -340,16 +348,25 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       fence_after_sync();
       float* vtile = vec + (size_t)(lt & 1) * vrows * vwidth;
       if (has_vec) {
-        if (vcol < vwidth) {
+        if (et < 128 && vcol < vwidth) {
 #pragma unroll
           for (int r = 0; r < 4; ++r)
             if (r < vrows) *reinterpret_cast<float4*>(vtile + r * vwidth + vcol) = pre[r];
         }
-        epi_bar_sync();  // vector visible to all four warps; also: everyone is done reading the tile before last's copy
+        epi_bar_sync();  // vector visible to all eight warps; also: everyone is done reading the tile before last's copy
       }
       const float* vrow = vtile + vr * vwidth;
-      for (int ps = 0; ps < passes; ++ps, ++g) {
-        const int buf = g % kG3Bufs;
+      if (ps0 >= passes) {  // no pass of this tile is ours: nothing to read from the accumulator
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+          else mbar_arrive(tempty_bar(acc));
+        }
+      }
+      for (int ps = ps0; ps < passes; ps += 2) {
+        const int g = g0 + ps;
+        const int buf = g & nb_mask;
         const int tc = pass_col(ps);          // column inside the tile's output slice
         uint32_t v[32];
         float f[32];
@@ -382,7 +399,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             }
           }
         }
-        if (ps + 1 == passes) {  // accumulator fully read: hand it back to the MMA warp (of the leader CTA)
+        if (ps == ps_last) {  // this warp's last read of the accumulator: hand it back to the MMA warp (of the leader CTA)
           fence_before_sync();
           __syncwarp();
           if (lane == 0) {  // (an arrive per thread would serialise 128 shared-memory atomics on one barrier)
@@ -391,7 +408,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
         }
         uint8_t* my_row = smem_gen + stg_off + (uint32_t)buf * kG3BufBytes + (uint32_t)row * 64u;
-        G3_TIMED(prof_on, w_grant, mbar_wait(res_bar(buf), (uint32_t)(g / kG3Bufs) & 1u));  // buffer granted (residual landed)
+        G3_TIMED(prof_on, w_grant, mbar_wait(res_bar(buf), (uint32_t)(g >> nb_shift) & 1u));  // buffer granted (residual landed)
         if (has_res) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -423,7 +440,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         if (lane == 0) mbar_arrive(stg_bar(buf));
       }
     }
-    if (prof_on && threadIdx.x == 64) { prof[8] = w_tfull; prof[9] = w_grant; prof[10] = clock64() - t_start; prof[11] = lt; }
+    if (prof_on && threadIdx.x == 128) { prof[8] = w_tfull; prof[9] = w_grant; prof[10] = clock64() - t_start; prof[11] = lt; }
   }
 
   // teardown: everyone (in both CTAs of a pair) done with TMEM before the allocating warp frees it

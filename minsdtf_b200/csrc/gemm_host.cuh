@@ -143,7 +143,7 @@ inline G3Plan plan_gemm3(int N, long long m_tiles, int act, int force_bn, int it
         if (cg == 2 && (m_tiles < 2 || (bn / n_mma / 2) % 8 != 0)) continue;
         if ((bn / n_mma) % 16 != 0) continue;
         const size_t stage = 16384 + (size_t)bn * 128 / cg;
-        if (3 * stage + 40000 > 232448) continue;  // at least 3 stages
+        if (3 * stage + 72000 > 232448) continue;  // at least 3 stages beside the staging buffers
         const long long units = ((m_tiles + cg - 1) / cg) * n_tiles;
         const long long slots = 148 / cg;
         const long long waves = (units + slots - 1) / slots;
@@ -153,7 +153,7 @@ inline G3Plan plan_gemm3(int N, long long m_tiles, int act, int force_bn, int it
         const double l2 = (double)stage / rate;
         const double t_iter = (mma > l2 ? mma : l2) + 30.0;
         const int ncols = geglu ? bn / 2 : bn;
-        const double t_epi = 300.0 + ((ncols + 31) / 32) * 280.0;
+        const double t_epi = 400.0 + ((ncols + 31) / 32) * 450.0;
         const double t_main = iters * t_iter;
         const double t_unit = bn > 256 ? t_main + t_epi : (t_main > t_epi ? t_main : t_epi) + 200.0;
         const double cost = (double)waves * t_unit * (cg == 2 && m_tiles % 2 ? 1.02 : 1.0);
@@ -234,6 +234,8 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       const size_t vec_bytes = (size_t)2 * x.vec_rows * x.vec_width * 4;
       const int cg = plan.cg;
       const size_t stage_bytes = kATileBytes + (size_t)(p.BN / cg) * 128;
+      x.nbufs = a.res ? kG3MaxBufs : 4;  // residual tiles are TMA-prefetched nbufs-1 passes ahead: latency needs depth
+      const int kG3Bufs = x.nbufs;
       const size_t fixed = 1024 + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * 10 + 4 + 2 * kG3Bufs) + 32 + vec_bytes;
       int st = (int)((kSmemLimit - fixed) / stage_bytes);
       if (st > 10) st = 10;

@@ -65,14 +65,30 @@ gn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, i
 #pragma unroll
   for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
   const bf16* base = x + ((long long)b * HW) * ld + cv * 8;
-  for (long long p = p0 + pl; p < p1; p += lanes) {
+  long long p = p0 + pl;
+  for (; p + 3LL * lanes < p1; p += 4LL * lanes) {  // four independent 16-byte loads in flight per thread
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (p + (long long)k * lanes) * ld);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f[8];
+      unpack8(u[k], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s[i] += f[i];
+        q[i] = fmaf(f[i], f[i], q[i]);
+      }
+    }
+  }
+  for (; p < p1; p += lanes) {
     const uint4 u = *reinterpret_cast<const uint4*>(base + p * ld);
     float f[8];
     unpack8(u, f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       s[i] += f[i];
-      q[i] += f[i] * f[i];
+      q[i] = fmaf(f[i], f[i], q[i]);
     }
   }
 #pragma unroll
@@ -81,21 +97,30 @@ gn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, i
     gn_sm[((pl * C) + cv * 8 + i) * 2 + 1] = q[i];
   }
   __syncthreads();
-  __shared__ bool is_last;
-  if (threadIdx.x < 32) {
-    const int g = threadIdx.x, gs = C >> 5;
-    double S = 0, Q = 0;
-    for (int l = 0; l < lanes; ++l)
-      for (int c = g * gs; c < (g + 1) * gs; ++c) {
+  // per-group reduction, one warp per group at a time: lane i adds items i, i+32, ... of the (lanes x gs) block in a
+  // fixed order, then a fixed shuffle tree — deterministic, and independent of how samples are batched
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, gs = C >> 5;
+    const int items = lanes * gs;
+    for (int g = warp; g < 32; g += nwarps) {
+      float S = 0.f, Q = 0.f;
+      for (int it = lane; it < items; it += 32) {
+        const int l = it / gs, c = g * gs + (it - l * gs);
         S += gn_sm[(l * C + c) * 2];
         Q += gn_sm[(l * C + c) * 2 + 1];
       }
-    double* dst = sc.partial + (((long long)b * kGnMaxBlk + blockIdx.x) * 32 + g) * 2;
-    dst[0] = S;
-    dst[1] = Q;
-    __threadfence();
+      S = warp_sum(S);
+      Q = warp_sum(Q);
+      if (lane == 0) {
+        double* dst = sc.partial + (((long long)b * kGnMaxBlk + blockIdx.x) * 32 + g) * 2;
+        dst[0] = (double)S;
+        dst[1] = (double)Q;
+      }
+    }
   }
+  __threadfence();
   __syncthreads();
+  __shared__ bool is_last;
   if (threadIdx.x == 0) {
     const unsigned ticket = atomicAdd(&sc.counters[b], 1u);
     is_last = (ticket == (unsigned)nblk - 1);
@@ -120,40 +145,50 @@ gn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, i
   }
 }
 
-__global__ void __launch_bounds__(256)
-gn_apply_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, const float* __restrict__ stats,
+// Phase 2: y = silu?((x - mean_g) * rstd_g * gamma_c + beta_c).  A thread owns one 8-channel vector for its whole pixel
+// range, so the per-channel scale / shift live in registers and the loop body is one 16-byte load, 8 FMAs (+ SiLU:
+// ex2 + rcp, two MUFU ops per element — tanh.approx was tried and cost parity on strongly negative inputs) and one
+// 16-byte store, four pixels in flight.
+__global__ void __launch_bounds__(512)
+gn_apply_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, int pix_per_cta, const float* __restrict__ stats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu, bf16* __restrict__ y,
                 long long ldy) {
-  const int b = blockIdx.y;
-  __shared__ float mean[32], rstd[32];
-  if (threadIdx.x < 32) {
-    mean[threadIdx.x] = stats[(long long)b * 64 + 2 * threadIdx.x];
-    rstd[threadIdx.x] = stats[(long long)b * 64 + 2 * threadIdx.x + 1];
-  }
-  __syncthreads();
   const int vecs = C >> 3, gs = C >> 5;
-  const long long total = HW * vecs;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / vecs;
-    const int cv = (int)(i - p * vecs);
-    const uint4 u = *reinterpret_cast<const uint4*>(x + ((long long)b * HW + p) * ld + cv * 8);
+  const int lanes = blockDim.x / vecs;
+  const int cv = threadIdx.x % vecs, pl = threadIdx.x / vecs;
+  const int b = blockIdx.y;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = cv * 8 + k, g = c / gs;
+    const float mean = stats[(long long)b * 64 + 2 * g], rstd = stats[(long long)b * 64 + 2 * g + 1];
+    const float a = rstd * __ldg(gamma + c);
+    sc[k] = a;
+    sh[k] = __ldg(beta + c) - mean * a;
+  }
+  const long long p0 = (long long)blockIdx.x * pix_per_cta;
+  const long long p1 = min(HW, p0 + pix_per_cta);
+  const bf16* xb = x + ((long long)b * HW) * ld + cv * 8;
+  bf16* yb = y + ((long long)b * HW) * ldy + cv * 8;
+  auto xform = [&](const uint4& u) {
     float f[8];
     unpack8(u, f);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8));
-    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + 4));
-    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int g = (cv * 8 + k) / gs;
-      float v = (f[k] - mean[g]) * rstd[g] * ga[k] + be[k];
-      if (silu) v = v / (1.f + __expf(-v));
-      f[k] = v;
+      const float h = fmaf(f[k], sc[k], sh[k]);
+      f[k] = silu ? __fdividef(h, 1.f + __expf(-h)) : h;
     }
-    *reinterpret_cast<uint4*>(y + ((long long)b * HW + p) * ldy + cv * 8) = pack8(f);
+    return pack8(f);
+  };
+  long long p = p0 + pl;
+  for (; p + 3LL * lanes < p1; p += 4LL * lanes) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (p + (long long)k * lanes) * ld);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(yb + (p + (long long)k * lanes) * ldy) = xform(u[k]);
   }
+  for (; p < p1; p += lanes) *reinterpret_cast<uint4*>(yb + p * ldy) = xform(*reinterpret_cast<const uint4*>(xb + p * ld));
 }
 
 static constexpr int kGnMaxBatch = 256;
@@ -169,7 +204,7 @@ inline void launch_groupnorm(cudaStream_t st, const View& x, const float* gamma,
   SDTF_CHECK(threads >= vecs && threads <= 512, "GroupNorm: unsupported channel count");
   const int lanes = threads / vecs;
   // CTAs per sample: a function of (HW, C) only, so statistics do not depend on how samples are batched
-  long long nblk = HW / (lanes * 4);
+  long long nblk = HW / (lanes * 8);
   if (nblk > kGnMaxBlk) nblk = kGnMaxBlk;
   if (nblk < 1) nblk = 1;
   const long long ppc = ceil_div_ll(HW, nblk);
@@ -178,12 +213,15 @@ inline void launch_groupnorm(cudaStream_t st, const View& x, const float* gamma,
   const size_t smem = (size_t)lanes * x.C * 2 * sizeof(float);
   gn_stats_kernel<<<g1, threads, smem, st>>>(x.p, x.ld, x.C, HW, (int)ppc, sc);
   SDTF_CUDA(cudaGetLastError());
-  const long long total = HW * vecs;
-  long long blocks = ceil_div_ll(total, 256 * 4);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  dim3 g2((unsigned)blocks, (unsigned)x.B);
-  gn_apply_kernel<<<g2, 256, 0, st>>>(x.p, x.ld, x.C, HW, sc.stats, gamma, beta, silu ? 1 : 0, y, ldy);
+  // apply: enough CTAs to cover the machine a few times over, each a contiguous pixel range
+  long long ablk = ceil_div_ll(148 * 4, x.B);
+  const long long max_blk = ceil_div_ll(HW, lanes * 4);
+  if (ablk > max_blk) ablk = max_blk;
+  if (ablk < 1) ablk = 1;
+  const long long appc = ceil_div_ll(HW, ablk);
+  ablk = ceil_div_ll(HW, appc);
+  dim3 g2((unsigned)ablk, (unsigned)x.B);
+  gn_apply_kernel<<<g2, threads, 0, st>>>(x.p, x.ld, x.C, HW, (int)appc, sc.stats, gamma, beta, silu ? 1 : 0, y, ldy);
   SDTF_CUDA(cudaGetLastError());
 }
 
@@ -194,45 +232,58 @@ template <int MAXV>  // max 8-channel vectors per lane
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const bf16* __restrict__ x, long long ld, int C, long long rows, const float* __restrict__ gamma,
                  const float* __restrict__ beta, bf16* __restrict__ y, long long ldy) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int vecs = C >> 3;
-  float f[MAXV][8];
-  float s = 0.f;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  // this lane's slice of gamma / beta stays in registers for every row the warp normalises
+  float ga[MAXV][8], be[MAXV][8];
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
     const int cv = lane + 32 * j;
     if (cv < vecs) {
-      const uint4 u = *reinterpret_cast<const uint4*>(x + row * ld + cv * 8);
-      unpack8(u, f[j]);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s += f[j][k];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + 4));
+      ga[j][0] = g0.x; ga[j][1] = g0.y; ga[j][2] = g0.z; ga[j][3] = g0.w; ga[j][4] = g1.x; ga[j][5] = g1.y; ga[j][6] = g1.z; ga[j][7] = g1.w;
+      be[j][0] = b0.x; be[j][1] = b0.y; be[j][2] = b0.z; be[j][3] = b0.w; be[j][4] = b1.x; be[j][5] = b1.y; be[j][6] = b1.z; be[j][7] = b1.w;
     }
   }
-  const float mean = warp_sum(s) / C;
-  float q = 0.f;
+  const float inv_c = 1.f / (float)C;
+  for (long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += nwarps) {
+    float f[MAXV][8];
+    float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int cv = lane + 32 * j;
-    if (cv < vecs) {
+    for (int j = 0; j < MAXV; ++j) {
+      const int cv = lane + 32 * j;
+      if (cv < vecs) {
+        const uint4 u = *reinterpret_cast<const uint4*>(x + row * ld + cv * 8);
+        unpack8(u, f[j]);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float d = f[j][k] - mean;
-        q += d * d;
+        for (int k = 0; k < 8; ++k) s += f[j][k];
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / C + 1e-5f);
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < MAXV; ++j) {
-    const int cv = lane + 32 * j;
-    if (cv < vecs) {
-      float o[8];
+    for (int j = 0; j < MAXV; ++j) {
+      const int cv = lane + 32 * j;
+      if (cv < vecs) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        o[k] = (f[j][k] - mean) * rstd * __ldg(gamma + cv * 8 + k) + __ldg(beta + cv * 8 + k);
-      *reinterpret_cast<uint4*>(y + row * ldy + cv * 8) = pack8(o);
+        for (int k = 0; k < 8; ++k) {
+          const float d = f[j][k] - mean;
+          q = fmaf(d, d, q);
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) * inv_c + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      const int cv = lane + 32 * j;
+      if (cv < vecs) {
+        float o[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o[k] = fmaf((f[j][k] - mean) * rstd, ga[j][k], be[j][k]);
+        *reinterpret_cast<uint4*>(y + row * ldy + cv * 8) = pack8(o);
+      }
     }
   }
 }
@@ -240,11 +291,12 @@ layernorm_kernel(const bf16* __restrict__ x, long long ld, int C, long long rows
 inline void launch_layernorm(cudaStream_t st, const bf16* x, long long ld, int C, long long rows, const float* gamma,
                              const float* beta, bf16* y, long long ldy) {
   SDTF_CHECK(C % 8 == 0 && C <= 32 * 8 * 5, "LayerNorm: C must be a multiple of 8 and <= 1280");
-  const unsigned blocks = (unsigned)ceil_div_ll(rows, 8);
+  long long blocks = ceil_div_ll(rows, 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;  // persistent warps: each keeps its gamma / beta slice and strides over rows
   const int vecs = C / 8;
-  if (vecs <= 64) layernorm_kernel<2><<<blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
-  else if (vecs <= 96) layernorm_kernel<3><<<blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
-  else layernorm_kernel<5><<<blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+  if (vecs <= 64) layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+  else if (vecs <= 96) layernorm_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+  else layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
   SDTF_CUDA(cudaGetLastError());
 }
 

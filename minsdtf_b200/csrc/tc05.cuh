@@ -47,16 +47,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return done != 0;
 }
-// Bounded wait: a pipeline bug becomes a trap (reported as a CUDA error) instead of a hung GPU.
+// Bounded wait: a pipeline bug becomes a trap (reported as a CUDA error) instead of a hung GPU.  The timeout clock is
+// only consulted every 4096 failed polls: reading %globaltimer on the wait path itself cost more than the wait
+// (measured: the attention kernel's barrier skeleton alone ran 0.85 ms with a timer read per slow-path entry).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = globaltimer_ns();
+  uint64_t t0 = 0;
   uint32_t it = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++it & 0x3ff) == 0 && globaltimer_ns() - t0 > 4000000000ull) {
-      printf("[sdtf] mbarrier timeout: block (%d,%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x,
-             blockIdx.y, blockIdx.z, threadIdx.x, bar, parity);
-      __trap();
+    if ((++it & 0xfff) == 0) {
+      const uint64_t now = globaltimer_ns();
+      if (t0 == 0) {
+        t0 = now;
+      } else if (now - t0 > 4000000000ull) {
+#ifdef SDTF_DEBUG_SYNC  // (a printf call on this path costs every caller registers and a stack frame)
+        printf("[sdtf] mbarrier timeout: block (%d,%d,%d) thread %d bar 0x%x parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x, bar, parity);
+#endif
+        __trap();
+      }
     }
   }
 }

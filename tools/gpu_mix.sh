@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/gpu_tests.log
+python bench.py --steps 3 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_engine.json 2> gpurun_out/bench_engine.err
+python - <<'PY'
+import json
+j=json.load(open('gpurun_out/bench_engine.json'))
+print({k:j[k] for k in ('value','ms_per_step','unet_step_ms','unet_step_tflops','decode_ms_per_batch','gpu_launches','clocks')}, j['e2e']['value'], j['roofline']['achieved'])
+PY
+python tools/ablate.py 2>&1 | tail -1 | tee gpurun_out/ablate.json
