@@ -91,12 +91,39 @@ inline int skip_mask() {
   return m;
 }
 
+// SDTF_TRACE=1 (debug, eager launches only): every operator is bracketed by CUDA events on the engine's stream and
+// one line per launch goes to stderr — kind, shape, microseconds, TFLOP/s and GB/s of algorithmic work — in graph order,
+// with the caches in the state the previous operator left them (unlike an ncu replay).  tools/trace_table.py sums it.
+inline bool trace_on() {
+  static const int v = getenv("SDTF_TRACE") ? atoi(getenv("SDTF_TRACE")) : 0;
+  return v != 0;
+}
+
 struct Ctx {
   cudaStream_t st = nullptr;
   Arena* ws = nullptr;
   bool dry = false;
   int launches = 0;
   GnScratch gn;
+
+  template <class F>
+  void traced(const char* kind, const std::string& shape, double flop, double bytes, F&& f) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (!trace_on() || dry || (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)) {
+      f();
+      return;
+    }
+    static cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (!e0) { SDTF_CUDA(cudaEventCreate(&e0)); SDTF_CUDA(cudaEventCreate(&e1)); }
+    SDTF_CUDA(cudaEventRecord(e0, st));
+    f();
+    SDTF_CUDA(cudaEventRecord(e1, st));
+    SDTF_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    SDTF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    fprintf(stderr, "[trace] %-6s %-44s %9.2f us %8.1f TFLOP/s %8.1f GB/s\n", kind, shape.c_str(), ms * 1e3, flop / (ms * 1e9),
+            bytes / (ms * 1e6));
+  }
 
   View alloc_view(int B, int H, int W, int C) {
     View v;
@@ -107,7 +134,17 @@ struct Ctx {
 
   void conv(const ConvArgs& a) {
     ++launches;
-    if (!dry && !(skip_mask() & SKIP_CONV)) launch_conv(st, a);
+    if (dry || (skip_mask() & SKIP_CONV)) return;
+    const PackedWeight& w = *a.w;
+    const int K = a.a0.C + (a.a1.p ? a.a1.C : 0);
+    const double M = (double)a.a0.B * a.outH * a.outW;
+    const int Nout = a.act == ACT_GEGLU ? w.N / 2 : w.N;
+    char buf[96];
+    snprintf(buf, sizeof buf, "%dx%dx%d %d%s->%d k%d s%d%s%s", a.a0.B, a.outH, a.outW, K, a.a1.p ? "(cat)" : "", w.N, w.kh, a.stride,
+             a.res ? " +res" : "", a.act == ACT_GEGLU ? " geglu" : "");
+    traced("conv", buf, 2.0 * M * w.N * K * w.kh * w.kw,
+           2.0 * ((double)a.a0.B * a.a0.H * a.a0.W * K + M * Nout * (a.res ? 2 : 1) + (double)w.N * K * w.kh * w.kw),
+           [&] { launch_conv(st, a); });
   }
   // y = conv(x) (+bias) (+temb) (+res) ; out view may be a channel slice
   void conv(const View& x, const PackedWeight& w, const View& out, int stride = 1, int pad = -1, const View* res = nullptr,
@@ -127,16 +164,27 @@ struct Ctx {
     conv(a);
   }
   void groupnorm(const View& x, const NormW& n, bool silu, const View& y) {
-    launches += 2;
-    if (!dry && !(skip_mask() & SKIP_GN)) launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn);
+    ++launches;
+    if (dry || (skip_mask() & SKIP_GN)) return;
+    char buf[64];
+    snprintf(buf, sizeof buf, "%dx%dx%dx%d%s", x.B, x.H, x.W, x.C, silu ? " silu" : "");
+    traced("gn", buf, 0.0, 4.0 * x.pixels() * x.C, [&] { launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn); });
   }
   void layernorm(const View& x, const NormW& n, const View& y) {
     ++launches;
-    if (!dry && !(skip_mask() & SKIP_LN)) launch_layernorm(st, x.p, x.ld, x.C, x.pixels(), n.gamma, n.beta, y.p, y.ld);
+    if (dry || (skip_mask() & SKIP_LN)) return;
+    char buf[64];
+    snprintf(buf, sizeof buf, "%lldx%d", x.pixels(), x.C);
+    traced("ln", buf, 0.0, 4.0 * x.pixels() * x.C,
+           [&] { launch_layernorm(st, x.p, x.ld, x.C, x.pixels(), n.gamma, n.beta, y.p, y.ld); });
   }
   void attention(const AttnArgs& a) {
     ++launches;
-    if (!dry && !(skip_mask() & SKIP_ATTN)) launch_attn(st, a);
+    if (dry || (skip_mask() & SKIP_ATTN)) return;
+    char buf[64];
+    snprintf(buf, sizeof buf, "B%d h%d Nq%d Nk%d d%d", a.B, a.heads, a.Nq, a.Nk, a.d);
+    traced("attn", buf, 4.0 * a.B * a.heads * (double)a.Nq * a.Nk * a.d,
+           2.0 * a.B * a.heads * a.d * (2.0 * a.Nq + 2.0 * a.Nk), [&] { launch_attn(st, a); });
   }
   void upsample2x(const View& x, const View& y) {
     ++launches;

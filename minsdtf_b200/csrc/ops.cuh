@@ -37,192 +37,232 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------------
 // GroupNorm(32 groups, eps 1e-5, biased variance) [+ SiLU]   (reference: keras GroupNormalization at
 // diffusion_model.py:27-28,32-33,57,277-278; layers.py:32,66-79; image_decoder.py:51-52)
-// Phase 1: per-(sample, group) sum / sum-of-squares.  Each thread owns one 8-channel vector position and
-// strides over pixels, so its loads are 16-byte and warp-contiguous.  Reduction is DETERMINISTIC and
-// independent of the batch size: per-thread partials -> smem -> 32 threads add them in a fixed order ->
-// one fp64 partial per (CTA, group); the last CTA of a sample (ticket counter) adds the CTA partials in
-// index order and publishes mean / rstd.  The number of CTAs per sample depends only on (H*W, C).
-// Phase 2: normalise + affine (+ SiLU) -> bf16.
+// ONE kernel per GroupNorm.  A sample is cut into nblk contiguous pixel ranges, one CTA each (nblk depends on
+// (H*W, C) only, so a sample's statistics do not depend on what it is batched with), and all CTAs of the launch are
+// co-resident (grid <= 2 CTAs per SM; larger batches are walked in rounds by the same CTAs):
+//   phase 1  per-thread sum / sum-of-squares of its 8-channel vector over the CTA's pixels (16-byte, warp-contiguous
+//            loads, four in flight) -> smem -> fixed-order per-channel, then per-group reduction -> one fp64 partial
+//            per (CTA, group), published to global memory;
+//   barrier  per-sample ticket counter + generation word (sense reversal); every CTA of the sample then adds the nblk
+//            partials in index order — DETERMINISTIC and identical in every CTA;
+//   phase 2  y = silu?((x - mean_g) * rstd_g * gamma_c + beta_c) over the same pixel range: the re-read hits L2 (the
+//            producer conv just wrote the tensor), so HBM sees one read and one write per element.
+// The previous two-kernel version (statistics, then apply) paid two launches, a serial last-CTA reduction and a
+// second cold ramp per GroupNorm: 3.2 ms of a 18.8 ms denoise step for 61 GroupNorms.
 // ------------------------------------------------------------------------------------------------------
 static constexpr int kGnMaxBlk = 64;
 
 struct GnScratch {
   double* partial = nullptr;    // [B][kGnMaxBlk][64]
   unsigned* counters = nullptr; // [B], zero between launches (self-resetting)
-  float* stats = nullptr;       // [B][64]: mean, rstd per group
+  unsigned* gens = nullptr;     // [B], barrier generation (monotonic)
+  float* stats = nullptr;       // [B][64]: mean, rstd per group (kept for debugging / tests)
 };
 
-__global__ void __launch_bounds__(512)
-gn_stats_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, int pix_per_cta, GnScratch sc) {
-  extern __shared__ float gn_sm[];  // [lanes][C][2]
-  const int vecs = C >> 3;
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(512, 2)
+gn_fused_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, int pix_per_cta, int B, GnScratch sc,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, bf16* __restrict__ y, long long ldy) {
+  extern __shared__ __align__(16) float gn_sm[];  // sums [lanes][C], then squares [lanes][C]
+  __shared__ float s_stats[64];
+  const int vecs = C >> 3, gs = C >> 5;
   const int lanes = blockDim.x / vecs;  // pixels processed in parallel by this CTA
   const int cv = threadIdx.x % vecs, pl = threadIdx.x / vecs;
-  const int b = blockIdx.y, nblk = gridDim.x;
+  const int nblk = gridDim.x;
+  float* smS = gn_sm;
+  float* smQ = gn_sm + lanes * C;
   const long long p0 = (long long)blockIdx.x * pix_per_cta;
   const long long p1 = min(HW, p0 + pix_per_cta);
-  float s[8], q[8];
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    unsigned gen0 = 0;
+    if (threadIdx.x == 0) gen0 = ld_acquire_gpu_u32(sc.gens + b);  // cannot advance before this CTA has arrived
+    // ---------------- phase 1 ----------------
+    float s[8], q[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-  const bf16* base = x + ((long long)b * HW) * ld + cv * 8;
-  long long p = p0 + pl;
-  for (; p + 3LL * lanes < p1; p += 4LL * lanes) {  // four independent 16-byte loads in flight per thread
-    uint4 u[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(base + (p + (long long)k * lanes) * ld);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
+    const bf16* xb = x + ((long long)b * HW) * ld + cv * 8;
+    long long p = p0 + pl;
+    auto accum = [&](const uint4& u) {
       float f[8];
-      unpack8(u[k], f);
+      unpack8(u, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         s[i] += f[i];
         q[i] = fmaf(f[i], f[i], q[i]);
       }
-    }
-  }
-  for (; p < p1; p += lanes) {
-    const uint4 u = *reinterpret_cast<const uint4*>(base + p * ld);
-    float f[8];
-    unpack8(u, f);
+    };
+    for (; p + 7LL * lanes < p1; p += 8LL * lanes) {  // eight independent 16-byte loads in flight per thread
+      uint4 u[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      s[i] += f[i];
-      q[i] = fmaf(f[i], f[i], q[i]);
-    }
-  }
+      for (int k = 0; k < 8; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (p + (long long)k * lanes) * ld);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    gn_sm[((pl * C) + cv * 8 + i) * 2] = s[i];
-    gn_sm[((pl * C) + cv * 8 + i) * 2 + 1] = q[i];
-  }
-  __syncthreads();
-  // per-group reduction, one warp per group at a time: lane i adds items i, i+32, ... of the (lanes x gs) block in a
-  // fixed order, then a fixed shuffle tree — deterministic, and independent of how samples are batched
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5, gs = C >> 5;
-    const int items = lanes * gs;
-    for (int g = warp; g < 32; g += nwarps) {
-      float S = 0.f, Q = 0.f;
-      for (int it = lane; it < items; it += 32) {
-        const int l = it / gs, c = g * gs + (it - l * gs);
-        S += gn_sm[(l * C + c) * 2];
-        Q += gn_sm[(l * C + c) * 2 + 1];
+      for (int k = 0; k < 8; ++k) accum(u[k]);
+    }
+    for (; p + 3LL * lanes < p1; p += 4LL * lanes) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (p + (long long)k * lanes) * ld);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) accum(u[k]);
+    }
+    for (; p < p1; p += lanes) accum(*reinterpret_cast<const uint4*>(xb + p * ld));
+    {
+      float4* dS = reinterpret_cast<float4*>(smS + pl * C + cv * 8);
+      float4* dQ = reinterpret_cast<float4*>(smQ + pl * C + cv * 8);
+      dS[0] = make_float4(s[0], s[1], s[2], s[3]); dS[1] = make_float4(s[4], s[5], s[6], s[7]);
+      dQ[0] = make_float4(q[0], q[1], q[2], q[3]); dQ[1] = make_float4(q[4], q[5], q[6], q[7]);
+    }
+    __syncthreads();
+    // per channel over the pixel lanes, fixed order (row 0 of each array receives the result)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float S = smS[c], Q = smQ[c];
+      for (int l = 1; l < lanes; ++l) {
+        S += smS[l * C + c];
+        Q += smQ[l * C + c];
       }
-      S = warp_sum(S);
-      Q = warp_sum(Q);
-      if (lane == 0) {
-        double* dst = sc.partial + (((long long)b * kGnMaxBlk + blockIdx.x) * 32 + g) * 2;
-        dst[0] = (double)S;
-        dst[1] = (double)Q;
+      smS[c] = S;
+      smQ[c] = Q;
+    }
+    __syncthreads();
+    // per group: one warp per group at a time, strided partial sums + a fixed shuffle tree
+    {
+      const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+      for (int g = warp; g < 32; g += nwarps) {
+        float S = 0.f, Q = 0.f;
+        for (int c = lane; c < gs; c += 32) {
+          S += smS[g * gs + c];
+          Q += smQ[g * gs + c];
+        }
+        S = warp_sum(S);
+        Q = warp_sum(Q);
+        if (lane == 0) {
+          double* dst = sc.partial + (((long long)b * kGnMaxBlk + blockIdx.x) * 32 + g) * 2;
+          dst[0] = (double)S;
+          dst[1] = (double)Q;
+        }
       }
     }
-  }
-  __threadfence();
-  __syncthreads();
-  __shared__ bool is_last;
-  if (threadIdx.x == 0) {
-    const unsigned ticket = atomicAdd(&sc.counters[b], 1u);
-    is_last = (ticket == (unsigned)nblk - 1);
-  }
-  __syncthreads();
-  if (is_last && threadIdx.x < 32) {
     __threadfence();
-    const int g = threadIdx.x;
-    double S = 0, Q = 0;
-    for (int k = 0; k < nblk; ++k) {
-      const volatile double* src = sc.partial + (((long long)b * kGnMaxBlk + k) * 32 + g) * 2;
-      S += src[0];
-      Q += src[1];
+    __syncthreads();
+    // ---------------- per-sample barrier ----------------
+    if (threadIdx.x == 0) {
+      const unsigned ticket = atomicAdd(&sc.counters[b], 1u);
+      if (ticket == (unsigned)nblk - 1) {
+        sc.counters[b] = 0;
+        __threadfence();
+        atomicAdd(&sc.gens[b], 1u);
+      } else {
+        unsigned spins = 0;
+        while (ld_acquire_gpu_u32(sc.gens + b) == gen0) {
+          if (++spins > (1u << 28)) __trap();  // a CTA of this sample is not resident: launch configuration bug
+        }
+      }
+      __threadfence();
     }
-    const double n = (double)HW * (C >> 5);
-    const double m = S / n;
-    double var = Q / n - m * m;
-    if (var < 0) var = 0;
-    sc.stats[(long long)b * 64 + 2 * g] = (float)m;
-    sc.stats[(long long)b * 64 + 2 * g + 1] = (float)(1.0 / sqrt(var + 1e-5));
-    if (g == 0) sc.counters[b] = 0;
-  }
-}
-
-// Phase 2: y = silu?((x - mean_g) * rstd_g * gamma_c + beta_c).  A thread owns one 8-channel vector for its whole pixel
-// range, so the per-channel scale / shift live in registers and the loop body is one 16-byte load, 8 FMAs (+ SiLU:
-// ex2 + rcp, two MUFU ops per element — tanh.approx was tried and cost parity on strongly negative inputs) and one
-// 16-byte store, four pixels in flight.
-__global__ void __launch_bounds__(512)
-gn_apply_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, int pix_per_cta, const float* __restrict__ stats,
-                const float* __restrict__ gamma, const float* __restrict__ beta, int silu, bf16* __restrict__ y,
-                long long ldy) {
-  const int vecs = C >> 3, gs = C >> 5;
-  const int lanes = blockDim.x / vecs;
-  const int cv = threadIdx.x % vecs, pl = threadIdx.x / vecs;
-  const int b = blockIdx.y;
-  float sc[8], sh[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int c = cv * 8 + k, g = c / gs;
-    const float mean = stats[(long long)b * 64 + 2 * g], rstd = stats[(long long)b * 64 + 2 * g + 1];
-    const float a = rstd * __ldg(gamma + c);
-    sc[k] = a;
-    sh[k] = __ldg(beta + c) - mean * a;
-  }
-  const long long p0 = (long long)blockIdx.x * pix_per_cta;
-  const long long p1 = min(HW, p0 + pix_per_cta);
-  const bf16* xb = x + ((long long)b * HW) * ld + cv * 8;
-  bf16* yb = y + ((long long)b * HW) * ldy + cv * 8;
-  auto xform = [&](const uint4& u) {
-    float f[8];
-    unpack8(u, f);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const int g = threadIdx.x >> 1, w = threadIdx.x & 1;
+      double acc = 0;
+      const double* src = sc.partial + ((long long)b * kGnMaxBlk * 32 + g) * 2 + w;
+      for (int k = 0; k < nblk; ++k) acc += __ldcg(src + (long long)k * 64);
+      const double other = __shfl_xor_sync(0xffffffffu, acc, 1);
+      const double S = w ? other : acc, Q = w ? acc : other;
+      const double n = (double)HW * gs;
+      const double m = S / n;
+      double var = Q / n - m * m;
+      if (var < 0) var = 0;
+      const float r = w ? (float)(1.0 / sqrt(var + 1e-5)) : (float)m;
+      s_stats[threadIdx.x] = r;
+      if (blockIdx.x == 0) sc.stats[(long long)b * 64 + threadIdx.x] = r;
+    }
+    __syncthreads();
+    // ---------------- phase 2 ----------------
+    float a8[8], h8[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float h = fmaf(f[k], sc[k], sh[k]);
-      f[k] = silu ? __fdividef(h, 1.f + __expf(-h)) : h;
+      const int c = cv * 8 + k, g = c / gs;
+      const float a = s_stats[2 * g + 1] * __ldg(gamma + c);
+      a8[k] = a;
+      h8[k] = __ldg(beta + c) - s_stats[2 * g] * a;
     }
-    return pack8(f);
-  };
-  long long p = p0 + pl;
-  for (; p + 3LL * lanes < p1; p += 4LL * lanes) {
-    uint4 u[4];
+    bf16* yb = y + ((long long)b * HW) * ldy + cv * 8;
+    auto xform = [&](const uint4& u) {
+      float f[8];
+      unpack8(u, f);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (p + (long long)k * lanes) * ld);
+      for (int k = 0; k < 8; ++k) {
+        const float h = fmaf(f[k], a8[k], h8[k]);
+        f[k] = silu ? __fdividef(h, 1.f + __expf(-h)) : h;
+      }
+      return pack8(f);
+    };
+    p = p0 + pl;
+    for (; p + 7LL * lanes < p1; p += 8LL * lanes) {
+      uint4 u[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(yb + (p + (long long)k * lanes) * ldy) = xform(u[k]);
+      for (int k = 0; k < 8; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (p + (long long)k * lanes) * ld);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) *reinterpret_cast<uint4*>(yb + (p + (long long)k * lanes) * ldy) = xform(u[k]);
+    }
+    for (; p + 3LL * lanes < p1; p += 4LL * lanes) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = *reinterpret_cast<const uint4*>(xb + (p + (long long)k * lanes) * ld);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) *reinterpret_cast<uint4*>(yb + (p + (long long)k * lanes) * ldy) = xform(u[k]);
+    }
+    for (; p < p1; p += lanes) *reinterpret_cast<uint4*>(yb + p * ldy) = xform(*reinterpret_cast<const uint4*>(xb + p * ld));
   }
-  for (; p < p1; p += lanes) *reinterpret_cast<uint4*>(yb + p * ldy) = xform(*reinterpret_cast<const uint4*>(xb + p * ld));
 }
 
 static constexpr int kGnMaxBatch = 256;
+static constexpr size_t kGnMaxSmem = 32 * 1024;  // lanes * C * 8 B <= 512 / (C / 8) * C * 8 B (static + dynamic stays under the 48 KB default)
+static int g_gn_resident_ctas = 0;  // CTAs of gn_fused_kernel that are co-resident on this device (set by init_norm_kernels)
 
-// x: NHWC view (possibly a slice of a wider buffer); y dense [B][HW][C] (ldy may differ)
-inline void launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, const float* beta, bool silu, bf16* y,
-                             long long ldy, const GnScratch& sc) {
+inline void init_norm_kernels() {
+  int dev = 0, sms = 0, occ = 0;
+  SDTF_CUDA(cudaGetDevice(&dev));
+  SDTF_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  SDTF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, gn_fused_kernel, 512, kGnMaxSmem));
+  SDTF_CHECK(occ >= 1, "gn_fused_kernel does not fit on an SM");
+  g_gn_resident_ctas = sms * (occ > 2 ? 2 : occ);
+}
+
+// x: NHWC view (possibly a slice of a wider buffer); y dense [B][HW][C] (ldy may differ).  Returns the launch count.
+inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, const float* beta, bool silu, bf16* y,
+                            long long ldy, const GnScratch& sc) {
   SDTF_CHECK(x.C % 32 == 0 && x.C % 8 == 0, "GroupNorm needs C % 32 == 0");
   SDTF_CHECK(x.B <= kGnMaxBatch, "GroupNorm: batch too large for the statistics scratch");
+  SDTF_CHECK(g_gn_resident_ctas > 0, "init_norm_kernels() was not called");
   const long long HW = (long long)x.H * x.W;
   const int vecs = x.C / 8;
   int threads = (512 / vecs) * vecs;
   SDTF_CHECK(threads >= vecs && threads <= 512, "GroupNorm: unsupported channel count");
   const int lanes = threads / vecs;
-  // CTAs per sample: a function of (HW, C) only, so statistics do not depend on how samples are batched
-  long long nblk = HW / (lanes * 8);
-  if (nblk > kGnMaxBlk) nblk = kGnMaxBlk;
+  const size_t smem = (size_t)lanes * x.C * 2 * sizeof(float);
+  SDTF_CHECK(smem <= kGnMaxSmem, "GroupNorm: reduction scratch exceeds the shared-memory budget the occupancy was computed for");
+  // CTAs per sample: a function of (HW, C) only, so statistics do not depend on how samples are batched.
+  // ~32 KB of the sample per CTA (four 16-byte vectors per thread: one round of loads per phase) up to 16 CTAs — a UNet
+  // batch of 16 is then one co-resident round on 148 SMs — and up to 32 for the VAE's 16+ MB samples.
+  const long long bytes = HW * x.C * 2;
+  long long nblk = ceil_div_ll(bytes, 32 * 1024);
+  if (nblk > 16) nblk = bytes > (16LL << 20) ? 32 : 16;
+  if (nblk > HW / lanes) nblk = HW / lanes;
   if (nblk < 1) nblk = 1;
   const long long ppc = ceil_div_ll(HW, nblk);
   nblk = ceil_div_ll(HW, ppc);
-  dim3 g1((unsigned)nblk, (unsigned)x.B);
-  const size_t smem = (size_t)lanes * x.C * 2 * sizeof(float);
-  gn_stats_kernel<<<g1, threads, smem, st>>>(x.p, x.ld, x.C, HW, (int)ppc, sc);
+  long long by = g_gn_resident_ctas / nblk;  // samples per round: every CTA of the grid must be resident
+  if (by > x.B) by = x.B;
+  SDTF_CHECK(by >= 1, "GroupNorm: a sample's CTAs do not fit on the device at once");
+  dim3 grid((unsigned)nblk, (unsigned)by);
+  gn_fused_kernel<<<grid, threads, smem, st>>>(x.p, x.ld, x.C, HW, (int)ppc, x.B, sc, gamma, beta, silu ? 1 : 0, y, ldy);
   SDTF_CUDA(cudaGetLastError());
-  // apply: enough CTAs to cover the machine a few times over, each a contiguous pixel range
-  long long ablk = ceil_div_ll(148 * 4, x.B);
-  const long long max_blk = ceil_div_ll(HW, lanes * 4);
-  if (ablk > max_blk) ablk = max_blk;
-  if (ablk < 1) ablk = 1;
-  const long long appc = ceil_div_ll(HW, ablk);
-  ablk = ceil_div_ll(HW, appc);
-  dim3 g2((unsigned)ablk, (unsigned)x.B);
-  gn_apply_kernel<<<g2, threads, 0, st>>>(x.p, x.ld, x.C, HW, (int)appc, sc.stats, gamma, beta, silu ? 1 : 0, y, ldy);
-  SDTF_CUDA(cudaGetLastError());
+  return 1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -288,15 +328,90 @@ layernorm_kernel(const bf16* __restrict__ x, long long ld, int C, long long rows
   }
 }
 
+// C == 8 * G * VPL: a row is normalised by a group of G lanes (G = 8 / 16 / 32 for C = 320 / 640 / 1280 at VPL = 5), so
+// a warp works on 32 / G rows at once with every lane busy (the one-warp-per-row kernel above leaves 3 lanes in 8 idle
+// at C = 320 and walks its rows one memory round trip at a time).  gamma / beta sit in shared memory.
+template <int G, int VPL>
+__global__ void __launch_bounds__(256)
+layernorm_group_kernel(const bf16* __restrict__ x, long long ld, int C, long long rows, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, bf16* __restrict__ y, long long ldy) {
+  extern __shared__ __align__(16) float ln_sm[];  // gamma [C], beta [C]
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    ln_sm[i] = __ldg(gamma + i);
+    ln_sm[C + i] = __ldg(beta + i);
+  }
+  __syncthreads();
+  constexpr int R = 32 / G;
+  const int lane = threadIdx.x & 31, sub = lane / G, gl = lane % G;
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float inv_c = 1.f / (float)C;
+  for (long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R; row0 < rows; row0 += nwarps * R) {
+    const long long row = row0 + sub;
+    const bool valid = row < rows;
+    float f[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      uint4 u = make_uint4(0, 0, 0, 0);
+      if (valid) u = *reinterpret_cast<const uint4*>(x + row * ld + (gl + G * j) * 8);
+      unpack8(u, f[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += f[j][k];
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = f[j][k] - mean;
+        q = fmaf(d, d, q);
+      }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * inv_c + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+      const int c0 = (gl + G * j) * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(ln_sm + c0), g1 = *reinterpret_cast<const float4*>(ln_sm + c0 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(ln_sm + C + c0), b1 = *reinterpret_cast<const float4*>(ln_sm + C + c0 + 4);
+      const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = fmaf((f[j][k] - mean) * rstd, ga[k], be[k]);
+      if (valid) *reinterpret_cast<uint4*>(y + row * ldy + c0) = pack8(o);
+    }
+  }
+}
+
+template <int G, int VPL>
+inline void launch_layernorm_group(cudaStream_t st, const bf16* x, long long ld, int C, long long rows, const float* gamma,
+                                   const float* beta, bf16* y, long long ldy) {
+  constexpr int R = 32 / G;
+  long long blocks = ceil_div_ll(rows, 8 * R);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  layernorm_group_kernel<G, VPL><<<(unsigned)blocks, 256, (size_t)C * 2 * sizeof(float), st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+}
+
 inline void launch_layernorm(cudaStream_t st, const bf16* x, long long ld, int C, long long rows, const float* gamma,
                              const float* beta, bf16* y, long long ldy) {
   SDTF_CHECK(C % 8 == 0 && C <= 32 * 8 * 5, "LayerNorm: C must be a multiple of 8 and <= 1280");
-  long long blocks = ceil_div_ll(rows, 8);
-  if (blocks > 148 * 8) blocks = 148 * 8;  // persistent warps: each keeps its gamma / beta slice and strides over rows
   const int vecs = C / 8;
-  if (vecs <= 64) layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
-  else if (vecs <= 96) layernorm_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
-  else layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+  if (C == 320) launch_layernorm_group<8, 5>(st, x, ld, C, rows, gamma, beta, y, ldy);
+  else if (C == 640) launch_layernorm_group<16, 5>(st, x, ld, C, rows, gamma, beta, y, ldy);
+  else if (C == 1280) launch_layernorm_group<32, 5>(st, x, ld, C, rows, gamma, beta, y, ldy);
+  else {
+    long long blocks = ceil_div_ll(rows, 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;  // persistent warps: each keeps its gamma / beta slice and strides over rows
+    if (vecs <= 64) layernorm_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+    else if (vecs <= 96) layernorm_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+    else layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+  }
   SDTF_CUDA(cudaGetLastError());
 }
 

@@ -211,11 +211,14 @@ int sdtf_create(int32_t device, sdtf_engine** out) {
     SDTF_CUDA(cudaMalloc((void**)&e->gn.counters, sizeof(unsigned) * kGnMaxBatch));
     SDTF_CUDA(cudaMalloc((void**)&e->gn.stats, sizeof(float) * 64 * kGnMaxBatch));
     SDTF_CUDA(cudaMemset(e->gn.counters, 0, sizeof(unsigned) * kGnMaxBatch));
+    SDTF_CUDA(cudaMalloc((void**)&e->gn.gens, sizeof(unsigned) * kGnMaxBatch));
+    SDTF_CUDA(cudaMemset(e->gn.gens, 0, sizeof(unsigned) * kGnMaxBatch));
     SDTF_CUDA(cudaMalloc((void**)&e->step_dev, sizeof(int) * 4));
     for (auto& ev : e->ev) SDTF_CUDA(cudaEventCreate(&ev));
     // kernel attributes are set up-front so that nothing but launches happens under stream capture
     init_gemm_kernels();
     init_attn_kernels();
+    init_norm_kernels();
     tensor_map_encoder();
   } catch (const std::exception& ex) {
     g_create_error = ex.what();
@@ -239,6 +242,7 @@ void sdtf_destroy(sdtf_engine* e) {
   if (e->ws.base) cudaFree(e->ws.base);
   cudaFree(e->gn.partial);
   cudaFree(e->gn.counters);
+  cudaFree(e->gn.gens);
   cudaFree(e->gn.stats);
   cudaFree(e->step_dev);
   for (auto& ev : e->ev) cudaEventDestroy(ev);

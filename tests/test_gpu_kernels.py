@@ -72,7 +72,8 @@ def _check_attention(engine, B, Nq, Nk, heads, d, legacy):
 @pytest.mark.parametrize("B,H,W,C,mode", [
     (2, 64, 64, 320, 1), (2, 32, 32, 640, 0), (2, 16, 16, 1280, 1), (2, 8, 8, 2560, 1), (1, 32, 32, 960, 1),
     (1, 16, 16, 1920, 1), (1, 128, 128, 128, 1), (1, 64, 64, 512, 0), (3, 24, 24, 256, 1),
-    (2, 64, 64, 320, 2), (2, 32, 32, 640, 2), (2, 16, 16, 1280, 2),
+    (2, 64, 64, 320, 2), (2, 32, 32, 640, 2), (2, 16, 16, 1280, 2), (1, 5, 7, 320, 2), (1, 5, 7, 640, 2), (1, 3, 3, 1280, 2),
+    (1, 8, 8, 768, 2), (16, 8, 8, 1280, 1), (18, 16, 16, 640, 0), (20, 8, 8, 320, 1),
 ])
 def test_norms_match_torch(engine, B, H, W, C, mode):
     g = torch.Generator().manual_seed(C + mode)

@@ -1,7 +1,9 @@
 #!/bin/bash
-# quick GPU visit: parity tests, engine bench (no CPU baseline), per-class ablation
+# parity tests + SDTF_TRACE operator table of 2 eager denoise steps + bench
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/gpu_tests.log
+SDTF_TRACE=1 python bench.py --steps 1 --warmup 1 --denoise-steps 2 --no-graph --skip-cpu-baseline --profile-only > gpurun_out/trace.out 2> gpurun_out/trace.log
+tail -1 gpurun_out/trace.out
 timeout 600 python bench.py --steps 3 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_engine.json 2> gpurun_out/bench_engine.err
 tail -3 gpurun_out/bench_engine.err
 python - <<'PY'
@@ -9,6 +11,3 @@ import json
 j=json.load(open('gpurun_out/bench_engine.json'))
 print({k:j[k] for k in ('value','ms_per_step','unet_step_ms','unet_step_tflops','decode_ms_per_batch','gpu_launches','clocks')}, j['e2e'], j['roofline']['achieved'])
 PY
-timeout 600 python tools/ablate.py 2>&1 | tail -1 | tee gpurun_out/ablation.json
-# attention variants (SDTF_ATTN_VAR): self-attention 64x64 micro-benchmark per variant
-for v in ${ATTN_VARS:-}; do echo "ATTN_VAR $v"; SDTF_ATTN_VAR=$v timeout 300 python tools/bench_kernels.py attn 2>&1 | grep -E '"legacy": false' | grep -E 'self 64x64|self 96x96|cross 64x64' ; done | tee gpurun_out/attn_vars.log
