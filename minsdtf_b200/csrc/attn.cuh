@@ -64,6 +64,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   const int nkv = (p.Nk + 127) / 128;
   const bool leader = threadIdx.x == 0;
 
+  pdl_trigger();
   if (leader) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(o_full, 1);
@@ -76,6 +77,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();  // Q / K / V come from the projection GEMMs
   const uint32_t tS = tmem, tO = tmem + 128;
 
   auto load_k = [&](int j) {
@@ -608,6 +610,7 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int col0 = head * p.dstride;
   const int nkv = (p.Nk + 127) / 128;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
@@ -625,6 +628,7 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();  // Q / K / V come from the projection GEMMs
 
   auto keys_in_tile = [&](int j) {  // valid keys of tile j rounded up to the MMA granularity
     int n = p.Nk - j * 128;
@@ -900,7 +904,7 @@ inline void launch_attn_t(cudaStream_t stream, const AttnArgs& a, const AttnPara
   auto kern = attn_kernel<DCH, KS, DV, KST, VST>;
   constexpr size_t smem = attn_smem_bytes<DCH, KST, VST>();
   dim3 grid((unsigned)ceil_div(a.Nq, 128), (unsigned)a.heads, (unsigned)a.B);
-  kern<<<grid, 128, smem, stream>>>(tq, tk, tv, p);
+  launch_pdl(kern, grid, dim3(128), smem, stream, 1, tq, tk, tv, p);
   SDTF_CUDA(cudaGetLastError());
 }
 
@@ -932,7 +936,7 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
       static const int use_2q = getenv("SDTF_ATTN_2Q") ? atoi(getenv("SDTF_ATTN_2Q")) : 0;  // A/B: previous full-row kernel
       if (!use_2q) {
         SDTF_CHECK(a.d < 48, "attn2h keeps the softmax denominator in accumulator column d: needs d < DV");
-        attn2h_kernel<3, 48><<<grid, kAHThreads, attn2h_smem_bytes(), stream>>>(tq, tk, tv, p);
+        launch_pdl(attn2h_kernel<3, 48>, grid, dim3(kAHThreads), attn2h_smem_bytes(), stream, 1, tq, tk, tv, p);
         SDTF_CUDA(cudaGetLastError());
         return;
       }

@@ -103,6 +103,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   long long* prof = prof_on ? x.prof + (long long)blockIdx.x * 16 : nullptr;
   const long long t_start = prof_on ? clock64() : 0;
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA0);
     prefetch_tmap(&tmB);
@@ -132,6 +133,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast commit
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // activations, residual and the time-embedding table come from earlier kernels of the stream
 
   // unit u -> this CTA's tile: n tile and the pixel box origin (out of range for the phantom tile of an odd pair)
   auto tile_coords = [&](int u, int& n_tile, int& x0, int& y0, int& b0) {

@@ -261,21 +261,8 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
         SDTF_CUDA(cudaMemsetAsync(prof_buf, 0, sizeof(long long) * 16 * 160, stream));
         x.prof = prof_buf;
       }
-      if (cg == 2) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(grid);
-        cfg.blockDim = dim3(kG3Threads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        SDTF_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm3_kernel<2>, tmA0, tmA1, tmB, tmOut, tmRes, p, x));
-      } else {
-        conv_gemm3_kernel<1><<<grid, kG3Threads, smem, stream>>>(tmA0, tmA1, tmB, tmOut, tmRes, p, x);
-      }
+      if (cg == 2) launch_pdl(conv_gemm3_kernel<2>, dim3(grid), dim3(kG3Threads), smem, stream, 2, tmA0, tmA1, tmB, tmOut, tmRes, p, x);
+      else launch_pdl(conv_gemm3_kernel<1>, dim3(grid), dim3(kG3Threads), smem, stream, 1, tmA0, tmA1, tmB, tmOut, tmRes, p, x);
       SDTF_CUDA(cudaGetLastError());
       if (profile) {
         SDTF_CUDA(cudaStreamSynchronize(stream));

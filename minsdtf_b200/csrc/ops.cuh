@@ -70,6 +70,8 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, i
                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu, bf16* __restrict__ y, long long ldy) {
   extern __shared__ __align__(16) float gn_sm[];  // sums [lanes][C], then squares [lanes][C]
   __shared__ float s_stats[64];
+  pdl_trigger();
+  pdl_wait();  // x, and the barrier words of the previous GroupNorm
   const int vecs = C >> 3, gs = C >> 5;
   const int lanes = blockDim.x / vecs;  // pixels processed in parallel by this CTA
   const int cv = threadIdx.x % vecs, pl = threadIdx.x / vecs;
@@ -260,7 +262,7 @@ inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, 
   if (by > x.B) by = x.B;
   SDTF_CHECK(by >= 1, "GroupNorm: a sample's CTAs do not fit on the device at once");
   dim3 grid((unsigned)nblk, (unsigned)by);
-  gn_fused_kernel<<<grid, threads, smem, st>>>(x.p, x.ld, x.C, HW, (int)ppc, x.B, sc, gamma, beta, silu ? 1 : 0, y, ldy);
+  launch_pdl(gn_fused_kernel, grid, dim3(threads), smem, st, 1, x.p, x.ld, x.C, HW, (int)ppc, x.B, sc, gamma, beta, silu ? 1 : 0, y, ldy);
   SDTF_CUDA(cudaGetLastError());
   return 1;
 }
@@ -336,11 +338,13 @@ __global__ void __launch_bounds__(256)
 layernorm_group_kernel(const bf16* __restrict__ x, long long ld, int C, long long rows, const float* __restrict__ gamma,
                        const float* __restrict__ beta, bf16* __restrict__ y, long long ldy) {
   extern __shared__ __align__(16) float ln_sm[];  // gamma [C], beta [C]
+  pdl_trigger();
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
     ln_sm[i] = __ldg(gamma + i);
     ln_sm[C + i] = __ldg(beta + i);
   }
   __syncthreads();
+  pdl_wait();
   constexpr int R = 32 / G;
   const int lane = threadIdx.x & 31, sub = lane / G, gl = lane % G;
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -395,7 +399,8 @@ inline void launch_layernorm_group(cudaStream_t st, const bf16* x, long long ld,
   constexpr int R = 32 / G;
   long long blocks = ceil_div_ll(rows, 8 * R);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  layernorm_group_kernel<G, VPL><<<(unsigned)blocks, 256, (size_t)C * 2 * sizeof(float), st>>>(x, ld, C, rows, gamma, beta, y, ldy);
+  launch_pdl(layernorm_group_kernel<G, VPL>, dim3((unsigned)blocks), dim3(256), (size_t)C * 2 * sizeof(float), st, 1, x, ld, C, rows, gamma,
+             beta, y, ldy);
 }
 
 inline void launch_layernorm(cudaStream_t st, const bf16* x, long long ld, int C, long long rows, const float* gamma,
