@@ -84,6 +84,14 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel_label):
+    """DRAM bytes per launch of the roofline kernel from the committed ncu --set full capture (profiles/ncu_traffic.json)"""
+    try:
+        return int(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel_label]["traffic"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -158,7 +166,7 @@ def run_reference(args, rank):
                                    "CPU restatement of the reference Keras graphs (keras/tensorflow not installable offline)"},
             "cpu_baseline": {"value": v, "unit": "images/s", "cores": meta[0], "kind": "port", "sample": meta[1]},
             "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -211,7 +219,7 @@ def run_engine(args, rank, world, local_rank):
         for _ in range(args.warmup + args.steps):
             resident_step()
         torch.cuda.synchronize()
-        print(json.dumps({"profile_only": True, "timings": eng.timings()}), flush=True)
+        emit({"profile_only": True, "timings": eng.timings()})
         return
 
     # ---- device-resident arm ----
@@ -287,6 +295,7 @@ def run_engine(args, rank, world, local_rank):
         # dominant kernel, timed alone with CUDA events on the engine's stream (rotating > L2 worth of operands)
         conv_ms = eng.bench_conv(2 * B, 64, 320, 320, 3, reps=40)
         conv_tflops = CONV_GFLOP * 2 * B / conv_ms
+        conv_label = "conv_gemm3_kernel 3x3 320->320 @64x64, batch %d" % (2 * B)
         line = {
             "metric": "images_per_second", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -303,7 +312,7 @@ def run_engine(args, rank, world, local_rank):
             "unet_step_ms": unet_step_ms, "unet_step_tflops": unet_tflops, "unet_step_frac_of_peak": unet_tflops / peak,
             "decode_ms_per_batch": dec_ms / K, "wall_ms_per_step": wall / K * 1e3,
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
-                         "traffic": None, "kernel": "conv_gemm3_kernel 3x3 320->320 @64x64, batch %d" % (2 * B),
+                         "traffic": ncu_traffic(conv_label), "kernel": conv_label,
                          "flop_per_launch": CONV_GFLOP * 2 * B * 1e9, "ms_per_launch": conv_ms, "peak_source": peak_src},
             "clocks": clocks,
         }
@@ -314,14 +323,31 @@ def run_engine(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line goes to the real stdout; everything else any library prints (NCCL's version banner, torchrun
+    notices) was redirected to stderr in main()"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # C-level writes to fd 1 (e.g. "NCCL version ...") must not pollute the JSON line
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
