@@ -282,20 +282,24 @@ static constexpr int kA2Threads = 352;
     }                                          \
   } while (0)
 
-template <int KS, int DV>
+// DCH = 64-column chunks per head row (1: d <= 64, 2: d = 80), KS = k-steps of Q K^T, DV = accumulator columns of P V,
+// KST / VST = K / V ring depth.  d = 80 (the 32x32 level, N = 1024) runs <2, 5, 80, 2, 1>: 14 chunks of shared memory;
+// V is single-buffered because P V_j only needs V_j one softmax pass after Q K^T_j needed K_j.
+template <int DCH, int KS, int DV, int KST, int VST>
 __global__ void __launch_bounds__(kA2Threads, 1)
 attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using namespace tc05;
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t kChunk = 128 * 128;  // [128 rows][64 bf16] swizzled = 16 KB
-  constexpr int KST = 3, VST = 3;
   constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kOStride = DV <= 64 ? 64u : 128u;  // accumulator g at TMEM column 256 + kOStride * g
+  static_assert(DV <= 128, "S (2 x 128 columns) and O (2 x kOStride) must fit the 512 TMEM columns");
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sQ = base;                       // 2 chunks
-  const uint32_t sK = sQ + 2 * kChunk;            // KST chunks
-  const uint32_t sV = sK + KST * kChunk;          // VST chunks
-  const uint32_t sP = sV + VST * kChunk;          // 2 groups x 2 chunks
+  const uint32_t sQ = base;                          // 2 tiles x DCH chunks
+  const uint32_t sK = sQ + 2 * DCH * kChunk;         // KST x DCH chunks
+  const uint32_t sV = sK + KST * DCH * kChunk;       // VST x DCH chunks
+  const uint32_t sP = sV + VST * DCH * kChunk;       // 2 groups x 2 chunks
   const uint32_t bars = sP + 4 * kChunk;
   const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u + 8u * s; };
@@ -344,23 +348,28 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   if (warp == 10) {
     // ===== TMA producer =====
     if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * kChunk);
-      tma_load_3d(sQ, &tmQ, q_full, col0, q0, b);
-      tma_load_3d(sQ + kChunk, &tmQ, q_full, col0, q0 + 128, b);
+      mbar_expect_tx(q_full, 2 * DCH * kChunk);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c) {
+        tma_load_3d(sQ + c * kChunk, &tmQ, q_full, col0 + 64 * c, q0, b);
+        tma_load_3d(sQ + (DCH + c) * kChunk, &tmQ, q_full, col0 + 64 * c, q0 + 128, b);
+      }
       long long w_ke = 0, w_ve = 0;
       for (int j = 0; j < nkv; ++j) {
         const int ks = j % KST, vs = j % VST;
         A2_TIMED(w_ke, mbar_wait(k_empty(ks), ((uint32_t)(j / KST) & 1u) ^ 1u));
         if (p.debug & 64) mbar_arrive(k_full(ks));
         else {
-          mbar_expect_tx(k_full(ks), kChunk);
-          tma_load_3d(sK + ks * kChunk, &tmK, k_full(ks), col0, j * 128, b);
+          mbar_expect_tx(k_full(ks), DCH * kChunk);
+#pragma unroll
+          for (int c = 0; c < DCH; ++c) tma_load_3d(sK + (ks * DCH + c) * kChunk, &tmK, k_full(ks), col0 + 64 * c, j * 128, b);
         }
         A2_TIMED(w_ve, mbar_wait(v_empty(vs), ((uint32_t)(j / VST) & 1u) ^ 1u));
         if (p.debug & 64) mbar_arrive(v_full(vs));
         else {
-          mbar_expect_tx(v_full(vs), kChunk);
-          tma_load_3d(sV + vs * kChunk, &tmV, v_full(vs), col0, j * 128, b);
+          mbar_expect_tx(v_full(vs), DCH * kChunk);
+#pragma unroll
+          for (int c = 0; c < DCH; ++c) tma_load_3d(sV + (vs * DCH + c) * kChunk, &tmV, v_full(vs), col0 + 64 * c, j * 128, b);
         }
       }
       if (prof_on) {
@@ -374,16 +383,19 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // ===== MMA issuer of group g = warp - 8 =====
     if (elect_one()) {
       const int g = warp - 8;
-      const uint32_t tS = tmem + 128u * g, tO = tmem + 256u + 64u * g;
-      const uint64_t dq = make_smem_desc_sw128(sQ + g * kChunk, 16, 1024);
+      const uint32_t tS = tmem + 128u * g, tO = tmem + 256u + kOStride * g;
+      const uint64_t dq = make_smem_desc_sw128(sQ + g * DCH * kChunk, 16, 1024);
       const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * g) * kChunk, 16, 1024);
       auto issue_qk = [&](int j) {
         const int st = j % KST;
         const uint32_t idesc = make_idesc_bf16(128, keys_in_tile(j), 0, 0);
-        const uint64_t dk = make_smem_desc_sw128(sK + st * kChunk, 16, 1024);
+        const uint64_t dk = make_smem_desc_sw128(sK + st * DCH * kChunk, 16, 1024);
         if (!(p.debug & 32)) {
 #pragma unroll
-          for (int k = 0; k < KS; ++k) mma_f16_ss(tS, dq + 2 * k, dk + 2 * k, idesc, k != 0);
+          for (int k = 0; k < KS; ++k) {  // k-step k: chunk k / 4, 32 bytes per step inside the 128-byte swizzled row
+            const uint64_t off = (uint64_t)((k >> 2) * (kChunk >> 4) + (k & 3) * 2);
+            mma_f16_ss(tS, dq + off, dk + off, idesc, k != 0);
+          }
         }
         mma_commit(s_full(g));
         mma_commit(k_empty(st));
@@ -408,7 +420,7 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const int ksteps = keys_in_tile(j) >> 4;
         for (int k = 0; k < ksteps && !(p.debug & 16); ++k) {
           const uint64_t da = dp + (uint64_t)((k >> 2) * (kChunk >> 4) + (k & 3) * 2);
-          const uint64_t db = make_smem_desc_sw128(sV + vs * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
+          const uint64_t db = make_smem_desc_sw128(sV + vs * DCH * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
           mma_f16_ss(tO, da, db, idesc_pv, (j | k) != 0);
         }
         mma_commit(o_done(g));
@@ -429,7 +441,7 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t tS = tmem + 128u * g + lane_off;
-    const uint32_t tO = tmem + 256u + 64u * g + lane_off;
+    const uint32_t tO = tmem + 256u + kOStride * g + lane_off;
     uint8_t* rowp = gen + (sP - base) + (uint32_t)(2 * g) * kChunk + row * 128;
     const int sw = row & 7;
     float m_run = -INFINITY, l_run = 0.f;
@@ -859,7 +871,10 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
 constexpr size_t attn2h_smem_bytes() { return 1024 + (size_t)(2 + 3 + 3 + 4) * 128 * 128 + 2048 + 8 + 8 * 12 + 96 + 8 * 3 + 16 + 16; }
 
-constexpr size_t attn2q_smem_bytes() { return 1024 + (size_t)(2 + 3 + 3 + 4) * 128 * 128 + 8 + 8 * 12 + 64 + 16; }
+template <int DCH, int KST, int VST>
+constexpr size_t attn2q_smem_bytes() {
+  return 1024 + (size_t)(2 * DCH + KST * DCH + VST * DCH + 4) * 128 * 128 + 8 + 8 * (2 * KST + 2 * VST) + 64 + 16;
+}
 
 template <int DCH, int KST, int VST>
 constexpr size_t attn_smem_bytes() {
@@ -892,7 +907,11 @@ inline void init_attn_t() {
 // called once per process before any launch (and before any stream capture)
 inline void init_attn_kernels() {
   init_attn_t<1, 3, 48, 2, 2>();
-  SDTF_CUDA(cudaFuncSetAttribute(attn2q_kernel<3, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2q_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2q_kernel<1, 3, 48, 3, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)attn2q_smem_bytes<1, 3, 3>()));
+  static_assert(attn2q_smem_bytes<2, 2, 1>() <= 232448, "d = 80 two-tile attention must fit 227 KB of shared memory");
+  SDTF_CUDA(cudaFuncSetAttribute(attn2q_kernel<2, 5, 80, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)attn2q_smem_bytes<2, 2, 1>()));
   SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
   init_attn_t<2, 5, 80, 2, 2>();
   init_attn_t<3, 10, 160, 1, 1>();
@@ -940,7 +959,7 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
         SDTF_CUDA(cudaGetLastError());
         return;
       }
-      attn2q_kernel<3, 48><<<grid, kA2Threads, attn2q_smem_bytes(), stream>>>(tq, tk, tv, p);
+      attn2q_kernel<1, 3, 48, 3, 3><<<grid, kA2Threads, attn2q_smem_bytes<1, 3, 3>(), stream>>>(tq, tk, tv, p);
       SDTF_CUDA(cudaGetLastError());
       if (p.prof) {  // debug: per-role wait cycles, averaged per CTA
         SDTF_CUDA(cudaStreamSynchronize(stream));
@@ -956,7 +975,12 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
     }
   } else if (a.d == 80) {
     SDTF_CHECK(a.dstride == 80, "d=80 heads are stored densely");
-    launch_attn_t<2, 5, 80, 2, 2>(stream, a, p, tq, tk, tv);
+    if (a.legacy) {
+      launch_attn_t<2, 5, 80, 2, 2>(stream, a, p, tq, tk, tv);
+    } else {  // two query tiles per CTA, warp-specialised (softmax of one tile overlaps the MMAs of the other)
+      dim3 grid((unsigned)ceil_div(a.Nq, 256), (unsigned)a.heads, (unsigned)a.B);
+      launch_pdl(attn2q_kernel<2, 5, 80, 2, 1>, grid, dim3(kA2Threads), attn2q_smem_bytes<2, 2, 1>(), stream, 1, tq, tk, tv, p);
+    }
   } else if (a.d == 160) {
     SDTF_CHECK(a.dstride == 160, "d=160 heads are stored densely");
     launch_attn_t<3, 10, 160, 1, 1>(stream, a, p, tq, tk, tv);

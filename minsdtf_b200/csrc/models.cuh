@@ -418,11 +418,13 @@ inline void encoder_half(Ctx& c, const EncoderHalfW& e, View* outs /*[12]*/, con
 }
 
 // UNet forward.  latent8: (B,h,w,8) bf16 (4 real channels), t_emb (B,320) f32 device, kv: projected context,
-// controls: null or 13 dense bf16 tensors, eps_out: (B,h,w,4) f32.
+// controls: null or 13 dense bf16 tensors, eps_out: (B,h,w,4) f32.  time_tab: optional precomputed [B][ncat] table of
+// the time-embedding MLP + per-ResBlock projections (the denoise loop computes it for every step before the loop: it
+// depends on the timestep only), in which case t_emb is not read.
 inline void unet_forward(Ctx& c, const UNetW& u, const bf16* latent8, int B, int h, int w, const float* t_emb, const CtxKV& kv,
-                         const bf16* const* controls, float* eps_out) {
+                         const bf16* const* controls, float* eps_out, const float* time_tab = nullptr) {
   const size_t m0 = c.ws->mark();
-  float* tab = time_table(c, u.enc.time, t_emb, B);
+  const float* tab = time_tab ? time_tab : time_table(c, u.enc.time, t_emb, B);
   const int tl = u.enc.time.ncat;
   // concat buffers cat[i] = [x (cx) | skip (cs)] at the resolution of up block i
   static const int cx[12] = {1280, 1280, 1280, 1280, 1280, 1280, 1280, 640, 640, 640, 320, 320};
@@ -490,9 +492,9 @@ inline void hintnet_forward(Ctx& c, const ControlNetW& cn, const bf16* image8, i
 
 // ControlNet (control_net.py:45-107): writes 13 dense bf16 residual tensors into res[i].
 inline void controlnet_forward(Ctx& c, const ControlNetW& cn, const bf16* latent8, int B, int h, int w, const float* t_emb,
-                               const CtxKV& kv, const View& hint, View* res /*[13]*/) {
+                               const CtxKV& kv, const View& hint, View* res /*[13]*/, const float* time_tab = nullptr) {
   const size_t m0 = c.ws->mark();
-  float* tab = time_table(c, cn.enc.time, t_emb, B);
+  const float* tab = time_tab ? time_tab : time_table(c, cn.enc.time, t_emb, B);
   const int tl = cn.enc.time.ncat;
   static const int ch[12] = {320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280};
   static const int lv[12] = {0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3};

@@ -681,20 +681,33 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
       c.ws->release(m);
     }
     c.cast_pad(latent, (long long)B * h * w, 4, 8, 1.f, lat8, dup);
+    // the time-embedding MLP and the 22 per-ResBlock projections depend on the timestep only: evaluated for all S
+    // steps here, once (52 MB of weights streamed once instead of every step); a step copies its row for each sample
+    const int ncat_u = e->unet.enc.time.ncat, ncat_c = control ? e->cnet.enc.time.ncat : 0;
+    const float* tab_all_u = time_table(c, e->unet.enc.time, temb_tab, S);
+    const float* tab_all_c = control ? time_table(c, e->cnet.enc.time, temb_tab, S) : nullptr;
+    float* tab_u = c.ws->alloc_n<float>((size_t)Bt * ncat_u);
+    float* tab_c = control ? c.ws->alloc_n<float>((size_t)Bt * ncat_c) : nullptr;
+    (void)temb_in;
 
     // ---- one denoising step ----
     auto step = [&](Ctx& sc) {
       ++sc.launches;
       if (!sc.dry) {
-        temb_select_kernel<<<ceil_div(Bt * 320, 256), 256, 0, e->st>>>(temb_tab, e->step_dev, 320, Bt, temb_in);
+        temb_select_kernel<<<ceil_div(Bt * ncat_u, 256), 256, 0, e->st>>>(tab_all_u, e->step_dev, ncat_u, Bt, tab_u);
         SDTF_CUDA(cudaGetLastError());
       }
       const bf16* cptr[13];
       if (control) {
-        controlnet_forward(sc, e->cnet, lat8, Bt, h, w, temb_in, kv_cn, hint, ctrl);
+        ++sc.launches;
+        if (!sc.dry) {
+          temb_select_kernel<<<ceil_div(Bt * ncat_c, 256), 256, 0, e->st>>>(tab_all_c, e->step_dev, ncat_c, Bt, tab_c);
+          SDTF_CUDA(cudaGetLastError());
+        }
+        controlnet_forward(sc, e->cnet, lat8, Bt, h, w, nullptr, kv_cn, hint, ctrl, tab_c);
         for (int i = 0; i < 13; ++i) cptr[i] = ctrl[i].p;
       }
-      unet_forward(sc, e->unet, lat8, Bt, h, w, temb_in, kv, control ? cptr : nullptr, eps + (split ? (size_t)srank * B * n : 0));
+      unet_forward(sc, e->unet, lat8, Bt, h, w, nullptr, kv, control ? cptr : nullptr, eps + (split ? (size_t)srank * B * n : 0), tab_u);
       if (split) {  // C1: in-place all-gather of this rank's branch; both ranks then run the update redundantly
         ++sc.launches;
         if (!sc.dry) {

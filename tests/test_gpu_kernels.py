@@ -37,6 +37,9 @@ def test_conv_gemm_standalone_cases():
     (2, 256, 77, 8, 160),
     (1, 1024, 154, 8, 80),     # long-prompt context (2 x 77)
     (1, 300, 200, 8, 40),      # ragged queries and keys
+    (1, 300, 200, 8, 80),      # ragged, two-tile d=80 kernel
+    (2, 576, 77, 8, 80),       # 768x768 level-1 cross-attention
+    (1, 2304, 2304, 4, 80),    # 768x768 level-1 self-attention
 ])
 def test_attention_matches_torch(engine, B, Nq, Nk, heads, d):
     _check_attention(engine, B, Nq, Nk, heads, d, legacy=False)

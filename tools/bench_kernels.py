@@ -19,7 +19,7 @@ def main():
         for (nq, nk, d, tag) in [(4096, 4096, 40, "self 64x64"), (4096, 77, 40, "cross 64x64"), (1024, 1024, 80, "self 32x32"),
                                  (1024, 77, 80, "cross 32x32"), (256, 256, 160, "self 16x16"), (9216, 9216, 40, "self 96x96 (B=4)")]:
             b = 4 if nq == 9216 else B
-            for legacy in ((False, True) if d == 40 else (False,)):
+            for legacy in ((False, True) if d in (40, 80) else (False,)):
                 ms = e.bench_attention(b, 8, nq, nk, d, reps=10, legacy=legacy)
                 fl = 4.0 * nq * nk * 8 * d * b
                 print(json.dumps({"kernel": "attention", "case": tag, "legacy": legacy, "B": b, "Nq": nq, "Nk": nk, "d": d, "ms": round(ms, 4),
