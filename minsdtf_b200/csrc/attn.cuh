@@ -881,6 +881,245 @@ constexpr size_t attn_smem_bytes() {
   return 1024 + (size_t)(DCH + KST * DCH + VST * DCH + 2) * 128 * 128 + 24 + 8 * (KST + VST) + 16;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// xattn: cross-attention with a short context (Nk <= 128 keys: the 77-token prompt).  The generic kernels spend a
+// whole CTA (TMEM allocation, barrier set-up, three TMA round trips) on ONE key tile per query tile — 2048 CTAs of
+// ~6 us of pure latency at the 64x64 level (97 us per launch for 84 MB of traffic).  Here one CTA owns a (sample,
+// head): K and V land in shared memory once, and the head's query tiles stream through a warp-specialised pipeline:
+//   warp 9      TMA: K, V, then a QST-deep ring of Q tiles
+//   warp 8      MMA: S_t = Q_t K^T into TMEM buffer t&1, then O_{t-1} = P_{t-1} V into accumulator (t-1)&1
+//   warps 0-3   softmax of tile t: a thread owns a row; one pass (all keys are in the tile: no running max, no
+//               rescale), row sum kept in registers and handed to the epilogue through shared memory
+//   warps 4-7   epilogue of tile t: O / l -> bf16 -> global, while the softmax warps are already on tile t+1
+// ------------------------------------------------------------------------------------------------------
+static constexpr int kXAThreads = 320;
+
+// NC = key columns the softmax code is compiled for (80: the 77-token prompt, 128: anything up to a full tile) — a
+// compile-time bound keeps the softmax one straight-line block the compiler can software-pipeline (one warp per
+// scheduler runs it: with warp-uniform branches around every 16-key block it ran at 3800 cycles per tile, 6x the MUFU floor)
+template <int DCH, int KS, int DV, int QST, int NC>
+__global__ void __launch_bounds__(kXAThreads, 1)
+xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+             const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using namespace tc05;
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kChunk = 128 * 128;
+  constexpr uint32_t kTmemCols = 512;
+  constexpr uint32_t kOStride = 128;  // accumulator b at TMEM column 256 + 128 b
+  static_assert(DV <= 128, "two S buffers (2 x 128 columns) and two accumulators (2 x 128) fill the 512 TMEM columns");
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = base;                        // DCH chunks
+  const uint32_t sV = sK + DCH * kChunk;           // DCH chunks
+  const uint32_t sQ = sV + DCH * kChunk;           // QST x DCH chunks
+  const uint32_t sP = sQ + QST * DCH * kChunk;     // 2 buffers x 2 chunks
+  const uint32_t sL = sP + 4 * kChunk;             // float [2][128]: row sums
+  const uint32_t bars = sL + 1024u;
+  const uint32_t kv_full = bars;
+  auto q_full = [&](int s) { return bars + 8u + 8u * s; };
+  auto q_empty = [&](int s) { return bars + 8u + 8u * (QST + s); };
+  const uint32_t bb = bars + 8u + 16u * QST;
+  auto s_full = [&](int b) { return bb + 8u * b; };
+  auto s_free = [&](int b) { return bb + 16u + 8u * b; };
+  auto p_full = [&](int b) { return bb + 32u + 8u * b; };
+  auto o_full = [&](int b) { return bb + 48u + 8u * b; };
+  auto o_free = [&](int b) { return bb + 64u + 8u * b; };
+  const uint32_t tmem_slot = bb + 80u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+  float* lbuf = reinterpret_cast<float*>(gen + (sL - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int col0 = head * p.dstride;
+  const int nqt = (p.Nq + 127) / 128;
+  const int ncols = (p.Nk + 15) & ~15;  // keys rounded up to the MMA granularity (TMA zero-fills the missing rows)
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < QST; ++s) { mbar_init(q_full(s), 1); mbar_init(q_empty(s), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1); mbar_init(s_free(i), 4);
+      mbar_init(p_full(i), 4); mbar_init(o_full(i), 1); mbar_init(o_free(i), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();  // Q comes from the projection GEMM of this step
+
+  if (warp == 9) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, 2 * DCH * kChunk);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c) {
+        tma_load_3d(sK + c * kChunk, &tmK, kv_full, col0 + 64 * c, 0, b);
+        tma_load_3d(sV + c * kChunk, &tmV, kv_full, col0 + 64 * c, 0, b);
+      }
+      for (int t = 0; t < nqt; ++t) {
+        const int st = t % QST;
+        if (t >= QST) mbar_wait(q_empty(st), (uint32_t)(t / QST - 1) & 1u);
+        mbar_expect_tx(q_full(st), DCH * kChunk);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + (st * DCH + c) * kChunk, &tmQ, q_full(st), col0 + 64 * c, t * 128, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      const uint32_t idesc_qk = make_idesc_bf16(128, ncols, 0, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
+      const uint64_t dk = make_smem_desc_sw128(sK, 16, 1024);
+      const int ksteps = ncols >> 4;
+      mbar_wait(kv_full, 0);
+      for (int t = 0; t <= nqt; ++t) {
+        if (t < nqt) {
+          const int st = t % QST, sb = t & 1, u = t >> 1;
+          mbar_wait(q_full(st), (uint32_t)(t / QST) & 1u);
+          if (u >= 1) mbar_wait(s_free(sb), (uint32_t)(u - 1) & 1u);  // S of tile t-2 is in registers
+          fence_after_sync();
+          const uint64_t dq = make_smem_desc_sw128(sQ + st * DCH * kChunk, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < KS; ++k) {
+            const uint64_t off = (uint64_t)((k >> 2) * (kChunk >> 4) + (k & 3) * 2);
+            mma_f16_ss(tmem + 128u * sb, dq + off, dk + off, idesc_qk, k != 0);
+          }
+          mma_commit(s_full(sb));
+          mma_commit(q_empty(st));
+        }
+        if (t >= 1) {
+          const int tp = t - 1, pb = tp & 1, u = tp >> 1;
+          mbar_wait(p_full(pb), (uint32_t)u & 1u);  // P of tile t-1 is in shared memory (and accumulator pb has been drained)
+          fence_after_sync();
+          const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * pb) * kChunk, 16, 1024);
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t da = dp + (uint64_t)((k >> 2) * (kChunk >> 4) + (k & 3) * 2);
+            const uint64_t db = make_smem_desc_sw128(sV + (uint32_t)k * 2048u, kChunk, 1024);
+            mma_f16_ss(tmem + 256u + kOStride * pb, da, db, idesc_pv, k != 0);
+          }
+          mma_commit(o_full(pb));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ===== softmax: thread = query row =====
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const int sw = row & 7;
+    for (int t = 0; t < nqt; ++t) {
+      const int sb = t & 1, u = t >> 1;
+      mbar_wait(s_full(sb), (uint32_t)u & 1u);
+      fence_after_sync();
+      constexpr int NL = (NC + 31) / 32 * 32;  // columns loaded (whole 32-column TMEM loads)
+      uint32_t sv[NL];
+      tmem_ld32_at<0>(tmem + 128u * sb + lane_off, sv);
+      if (NL > 32) tmem_ld32_at<(NL > 32 ? 32 : 0)>(tmem + 128u * sb + lane_off + 32, sv);
+      if (NL > 64) tmem_ld32_at<(NL > 64 ? 64 : 0)>(tmem + 128u * sb + lane_off + 64, sv);
+      if (NL > 96) tmem_ld32_at<(NL > 96 ? 96 : 0)>(tmem + 128u * sb + lane_off + 96, sv);
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free(sb));
+      // keys past the context (and columns the MMA never wrote) -> -inf: everything below is unpredicated straight-line code
+#pragma unroll
+      for (int i = 0; i < NC; ++i)
+        if (i >= p.Nk) sv[i] = 0xff800000u;
+      float mxa = -INFINITY, mxb = -INFINITY;  // two independent chains (one warp per scheduler: latency is not hidden)
+#pragma unroll
+      for (int c = 0; c < NC; c += 8) {
+        mxa = fmax3(mxa, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
+        mxb = fmax3(mxb, __uint_as_float(sv[c + 2]), __uint_as_float(sv[c + 3]));
+        mxa = fmax3(mxa, __uint_as_float(sv[c + 4]), __uint_as_float(sv[c + 5]));
+        mxb = fmax3(mxb, __uint_as_float(sv[c + 6]), __uint_as_float(sv[c + 7]));
+      }
+      const float scale = p.scale_log2;
+      const float neg_m = -fmaxf(mxa, mxb) * scale;
+      uint32_t pk[NC / 2];
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = ex2f(fmaf(__uint_as_float(sv[c + i]), scale, neg_m));
+        ls0 += e[0] + e[1]; ls1 += e[2] + e[3]; ls2 += e[4] + e[5]; ls3 += e[6] + e[7];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[(c >> 1) + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
+      }
+      if (u >= 1) {  // P V of tile t-2 has been read out by the epilogue: P buffer, row sums and accumulator sb are free
+        mbar_wait(o_free(sb), (uint32_t)(u - 1) & 1u);
+        fence_after_sync();
+      }
+      uint8_t* rowp = gen + (sP - base) + (uint32_t)(2 * sb) * kChunk + row * 128;
+#pragma unroll
+      for (int c = 0; c < NC; c += 8) {
+        const int chunk = c >> 6, un = (c & 63) >> 3;
+        *reinterpret_cast<uint4*>(rowp + chunk * kChunk + ((un ^ sw) << 4)) =
+            make_uint4(pk[(c >> 1)], pk[(c >> 1) + 1], pk[(c >> 1) + 2], pk[(c >> 1) + 3]);
+      }
+      const float lsum = (ls0 + ls1) + (ls2 + ls3);
+      lbuf[sb * 128 + row] = lsum;
+      fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(sb));
+    }
+  } else {
+    // ===== epilogue: O / l -> bf16 =====
+    const int q4 = warp - 4;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
+    for (int t = 0; t < nqt; ++t) {
+      const int ob = t & 1, u = t >> 1;
+      mbar_wait(p_full(ob), (uint32_t)u & 1u);  // release/acquire with the softmax threads: the row sums are visible
+      mbar_wait(o_full(ob), (uint32_t)u & 1u);
+      fence_after_sync();
+      uint32_t o[DV];
+#pragma unroll
+      for (int c = 0; c < DV; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem + 256u + kOStride * ob + lane_off + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c + i] = v[i];
+      }
+      tmem_ld_wait();
+      const float inv_l = 1.f / lbuf[ob * 128 + row];
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free(ob));
+      const int q = t * 128 + row;
+      if (q < p.Nq) {
+        bf16* orow = p.out + ((long long)b * p.Nq + q) * p.ldo + head * p.d;
+#pragma unroll
+        for (int c = 0; c < DV; c += 8) {
+          if (c + 8 <= p.d) {
+            uint4 w;
+            w.x = pack_bf16(__uint_as_float(o[c]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+            w.y = pack_bf16(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+            w.z = pack_bf16(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+            w.w = pack_bf16(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c) = w;
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, kTmemCols);
+}
+
+template <int DCH, int QST>
+constexpr size_t xattn_smem_bytes() {
+  return 1024 + (size_t)(2 * DCH + QST * DCH + 4) * 128 * 128 + 1024 + 8 + 16 * QST + 80 + 16;
+}
+
 // Q/K/V token matrices: [B][N][ld] bf16; head h of Q at q + h*dstride etc.
 struct AttnArgs {
   const bf16 *q, *k, *v;
@@ -915,6 +1154,11 @@ inline void init_attn_kernels() {
   SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
   init_attn_t<2, 5, 80, 2, 2>();
   init_attn_t<3, 10, 160, 1, 1>();
+  static_assert(xattn_smem_bytes<2, 3>() <= 232448, "d = 80 cross-attention must fit 227 KB of shared memory");
+  SDTF_CUDA(cudaFuncSetAttribute(xattn_kernel<1, 3, 48, 4, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem_bytes<1, 4>()));
+  SDTF_CUDA(cudaFuncSetAttribute(xattn_kernel<1, 3, 48, 4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem_bytes<1, 4>()));
+  SDTF_CUDA(cudaFuncSetAttribute(xattn_kernel<2, 5, 80, 3, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem_bytes<2, 3>()));
+  SDTF_CUDA(cudaFuncSetAttribute(xattn_kernel<2, 5, 80, 3, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem_bytes<2, 3>()));
 }
 
 template <int DCH, int KS, int DV, int KST, int VST>
@@ -946,6 +1190,21 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
   CUtensorMap tq = make_tok_tmap(a.q, cols, a.Nq, a.B, a.ldq);
   CUtensorMap tk = make_tok_tmap(a.k, cols, a.Nk, a.B, a.ldk);
   CUtensorMap tv = make_tok_tmap(a.v, cols, a.Nk, a.B, a.ldv);
+  // short contexts (the 77-token prompt): one CTA per (sample, head), K / V resident, query tiles pipelined
+  static const int use_xattn = getenv("SDTF_XATTN") ? atoi(getenv("SDTF_XATTN")) : 1;
+  if (use_xattn && !a.legacy && a.Nk <= 128 && a.Nq >= 256 && (a.d == 40 || a.d == 80)) {
+    dim3 grid((unsigned)a.heads, (unsigned)a.B);
+    if (a.d == 40) {
+      SDTF_CHECK(a.dstride == 64, "d=40 heads must be stored zero-padded to 64 columns");
+      if (a.Nk <= 80) launch_pdl(xattn_kernel<1, 3, 48, 4, 80>, grid, dim3(kXAThreads), xattn_smem_bytes<1, 4>(), stream, 1, tq, tk, tv, p);
+      else launch_pdl(xattn_kernel<1, 3, 48, 4, 128>, grid, dim3(kXAThreads), xattn_smem_bytes<1, 4>(), stream, 1, tq, tk, tv, p);
+    } else {
+      SDTF_CHECK(a.dstride == 80, "d=80 heads are stored densely");
+      if (a.Nk <= 80) launch_pdl(xattn_kernel<2, 5, 80, 3, 80>, grid, dim3(kXAThreads), xattn_smem_bytes<2, 3>(), stream, 1, tq, tk, tv, p);
+      else launch_pdl(xattn_kernel<2, 5, 80, 3, 128>, grid, dim3(kXAThreads), xattn_smem_bytes<2, 3>(), stream, 1, tq, tk, tv, p);
+    }
+    return;
+  }
   if (a.d == 40) {
     SDTF_CHECK(a.dstride == 64, "d=40 heads must be stored zero-padded to 64 columns");
     if (a.legacy) {

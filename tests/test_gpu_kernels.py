@@ -40,6 +40,12 @@ def test_conv_gemm_standalone_cases():
     (1, 300, 200, 8, 80),      # ragged, two-tile d=80 kernel
     (2, 576, 77, 8, 80),       # 768x768 level-1 cross-attention
     (1, 2304, 2304, 4, 80),    # 768x768 level-1 self-attention
+    (16, 4096, 77, 8, 40),     # resident-K/V cross-attention kernel at the benchmark shape
+    (3, 300, 77, 8, 40),       # ... ragged queries
+    (1, 1024, 128, 8, 80),     # ... full key tile
+    (2, 512, 16, 8, 40),       # ... tiny contexts
+    (1, 256, 1, 8, 40),
+    (2, 9216, 77, 8, 40),      # 768x768 level-0 cross-attention
 ])
 def test_attention_matches_torch(engine, B, Nq, Nk, heads, d):
     _check_attention(engine, B, Nq, Nk, heads, d, legacy=False)
