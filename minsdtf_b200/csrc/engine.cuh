@@ -132,8 +132,17 @@ struct Ctx {
     return v;
   }
 
-  void conv(const ConvArgs& a) {
+  void conv(const ConvArgs& a0) {
     ++launches;
+    // split-K scratch (fp32 partial sums) lives in the arena for the duration of the launch pair
+    ConvArgs a = a0;
+    const size_t sk_floats = a.splitk_ws ? 0 : conv_splitk_floats(a);
+    const size_t sk_mark = ws->mark();
+    if (sk_floats) {
+      a.splitk_ws = ws->alloc_n<float>(sk_floats);
+      ++launches;
+    }
+    struct Release { Arena* w; size_t m; ~Release() { w->release(m); } } rel{ws, sk_mark};
     if (dry || (skip_mask() & SKIP_CONV)) return;
     const PackedWeight& w = *a.w;
     const int K = a.a0.C + (a.a1.p ? a.a1.C : 0);

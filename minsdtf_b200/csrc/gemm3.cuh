@@ -44,6 +44,9 @@ struct Gemm3Extra {
   int nbufs;             // staging buffers in use (<= kG3MaxBufs)
   int vec_rows;          // rows of the per-tile epilogue vector staged in smem: samples a tile spans (time-embedding conv) or 1
   int vec_width;         // its width in floats (tile columns, rounded up to 32)
+  int splits;            // split-K: the k-iterations of a tile are cut into `splits` ranges, one unit each (1: off)
+  int iters_split;       // k-iterations per range (the last range may be shorter)
+  float* partial;        // split-K: fp32 partial sums [splits][B*H*W][N] (the reduce kernel applies the epilogue)
   long long* prof;       // optional [gridDim.x][16] cycle counters per role (null: off); see gemm_host.cuh
   int debug;             // timing experiments only (results are garbage): 1 = skip the MMA instructions, 2 = skip the TMA loads
 };
@@ -97,7 +100,8 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int kchunks = p.kc0 + p.kc1;
   const int iters = p.taps * kchunks;
   const int m_units = (x.m_tiles + CG - 1) / CG;
-  const int total_units = m_units * x.n_tiles;
+  const int total_units = m_units * x.n_tiles * x.splits;
+  const bool partial_mode = x.partial != nullptr;
   const int unit0 = (int)blockIdx.x / CG, unit_step = (int)gridDim.x / CG;
   const bool prof_on = x.prof != nullptr;
   long long* prof = prof_on ? x.prof + (long long)blockIdx.x * 16 : nullptr;
@@ -133,12 +137,18 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (CG == 2) cluster_sync_all();  // peer barriers initialised before any remote arrive / multicast commit
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // split-K: unit u covers k-iterations [i0, i0 + n_it) of its tile
+  auto k_range = [&](int u, int& i0, int& n_it) {
+    const int ks = (u / x.n_tiles) / m_units;
+    i0 = ks * x.iters_split;
+    n_it = iters - i0 < x.iters_split ? iters - i0 : x.iters_split;
+  };
   pdl_wait();  // activations, residual and the time-embedding table come from earlier kernels of the stream
 
   // unit u -> this CTA's tile: n tile and the pixel box origin (out of range for the phantom tile of an odd pair)
   auto tile_coords = [&](int u, int& n_tile, int& x0, int& y0, int& b0) {
     n_tile = u % x.n_tiles;
-    int mt = (u / x.n_tiles) * CG + (int)rank;
+    int mt = ((u / x.n_tiles) % m_units) * CG + (int)rank;
     const int tx = mt % p.tiles_x; mt /= p.tiles_x;
     const int ty = mt % p.tiles_y; mt /= p.tiles_y;
     x0 = tx * p.bw; y0 = ty * p.bh; b0 = mt * p.bn;
@@ -162,31 +172,35 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tile_coords(u, n_tile, x0, y0, b0);
         const int nrow0 = n_tile * p.BN + (int)(rank * chunk_rows);
         const int cx0 = x0 * p.stride - p.pad_x, cy0 = y0 * p.stride - p.pad_y;
-        int r = 0, sx = 0;
-        for (int tap = 0; tap < p.taps; ++tap) {
+        int i0, n_it;
+        k_range(u, i0, n_it);
+        int tap = i0 / kchunks, kc = i0 - tap * kchunks;  // (two divisions per tile, none per iteration)
+        int r = tap / p.tap_w, sx = tap - r * p.tap_w;
+        for (int it = 0; it < n_it; ++it) {
           const int cx = cx0 + sx, cy = cy0 + r;
-          for (int kc = 0; kc < kchunks; ++kc) {
-            G3_TIMED(prof_on, w_empty, mbar_wait(eb, ph ^ 1u));
-            const uint32_t sb = sa + kATileBytes;
-            const CUtensorMap* ta = kc < p.kc0 ? &tmA0 : &tmA1;
-            const int ka = (kc < p.kc0 ? kc : kc - p.kc0) * kBK;
-            if (x.debug & 2) {
-              if (rank == 0) mbar_arrive(fb);
-            } else if (CG == 1) {
-              mbar_expect_tx(fb, tx_bytes);
-              tma_load_4d(sa, ta, fb, ka, cx, cy, b0);
-              tma_load_3d(sb, &tmB, fb, kc * kBK, nrow0, tap);
-              if (x.n_mma == 2) tma_load_3d(sb + chunk_stride, &tmB, fb, kc * kBK, nrow0 + chunk, tap);
-            } else {
-              if (rank == 0) mbar_expect_tx(fb, tx_bytes);  // both CTAs' bytes land on the leader's barrier
-              tma_load_4d_pair(sa, ta, fb, ka, cx, cy, b0);
-              tma_load_3d_pair(sb, &tmB, fb, kc * kBK, nrow0, tap);
-              if (x.n_mma == 2) tma_load_3d_pair(sb + chunk_stride, &tmB, fb, kc * kBK, nrow0 + chunk, tap);
-            }
-            sa += stage_bytes; fb += 8u; eb += 8u;
-            if (++st == n_stages) { st = 0; ph ^= 1u; sa = smem_base; fb = full_bar(0); eb = empty_bar(0); }
+          G3_TIMED(prof_on, w_empty, mbar_wait(eb, ph ^ 1u));
+          const uint32_t sb = sa + kATileBytes;
+          const CUtensorMap* ta = kc < p.kc0 ? &tmA0 : &tmA1;
+          const int ka = (kc < p.kc0 ? kc : kc - p.kc0) * kBK;
+          if (x.debug & 2) {
+            if (rank == 0) mbar_arrive(fb);
+          } else if (CG == 1) {
+            mbar_expect_tx(fb, tx_bytes);
+            tma_load_4d(sa, ta, fb, ka, cx, cy, b0);
+            tma_load_3d(sb, &tmB, fb, kc * kBK, nrow0, tap);
+            if (x.n_mma == 2) tma_load_3d(sb + chunk_stride, &tmB, fb, kc * kBK, nrow0 + chunk, tap);
+          } else {
+            if (rank == 0) mbar_expect_tx(fb, tx_bytes);  // both CTAs' bytes land on the leader's barrier
+            tma_load_4d_pair(sa, ta, fb, ka, cx, cy, b0);
+            tma_load_3d_pair(sb, &tmB, fb, kc * kBK, nrow0, tap);
+            if (x.n_mma == 2) tma_load_3d_pair(sb + chunk_stride, &tmB, fb, kc * kBK, nrow0 + chunk, tap);
           }
-          if (++sx == p.tap_w) { sx = 0; ++r; }
+          sa += stage_bytes; fb += 8u; eb += 8u;
+          if (++st == n_stages) { st = 0; ph ^= 1u; sa = smem_base; fb = full_bar(0); eb = empty_bar(0); }
+          if (++kc == kchunks) {
+            kc = 0; ++tap;
+            if (++sx == p.tap_w) { sx = 0; ++r; }
+          }
         }
       }
       if (prof_on) { prof[0] = w_empty; prof[1] = clock64() - t_start; }
@@ -216,7 +230,9 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)x.acc_stride;
         const uint32_t d_tmem2 = d_tmem + (uint32_t)chunk;
-        for (int i = 0; i < iters; ++i) {
+        int i0, n_it;
+        k_range(u, i0, n_it);
+        for (int i = 0; i < n_it; ++i) {
           G3_TIMED(prof_on, w_full, mbar_wait(fb, ph));
           fence_after_sync();
           if (!skip) {
@@ -244,7 +260,8 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     __syncwarp();
   } else if (warp == 2) {
     // ===== store warp: TMA stores of staged sub-tiles; grants staging buffers (with the residual tile when there is one)
-    if (elect_one()) {
+    // (split-K partial sums leave straight from the epilogue warps' registers: nothing to stage)
+    if (!partial_mode && elect_one()) {
       const bool geglu = (p.act == ACT_GEGLU);
       const int ncols = x.ncols;
       const int passes = (ncols + 31) >> 5;
@@ -365,6 +382,38 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
           else mbar_arrive(tempty_bar(acc));
         }
+      }
+      if (partial_mode) {
+        // split-K: raw fp32 accumulator rows -> partial[ks][pixel][column]; bias / time embedding / residual / bf16
+        // rounding happen once, in splitk_reduce_kernel
+        const int ks = (u / x.n_tiles) / m_units;
+        const int rpb = 1 << x.log_rows_per_b;
+        const int rr = row & (rpb - 1);
+        const int pb = b0 + (row >> x.log_rows_per_b), py = y0 + rr / p.bw, px = x0 + rr % p.bw;
+        const bool row_ok = pb < p.B && py < p.H && px < p.W;
+        float* prow = x.partial + ((long long)ks * p.B * p.H * p.W + ((long long)pb * p.H + py) * p.W + px) * p.N +
+                      (long long)n_tile * ncols;
+        for (int ps = ps0; ps < passes; ps += 2) {
+          const int tc = pass_col(ps);
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)tc, v);
+          tmem_ld_wait();
+          if (ps == ps_last) {
+            fence_before_sync();
+            __syncwarp();
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+              else mbar_arrive(tempty_bar(acc));
+            }
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              if (n_tile * ncols + tc + i < p.N)
+                *reinterpret_cast<uint4*>(prow + tc + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+        continue;
       }
       for (int ps = ps0; ps < passes; ps += 2) {
         const int g = g0 + ps;

@@ -35,6 +35,7 @@ struct ConvArgs {
   int act = ACT_NONE;
   float out_scale = 1.f;
   int force_bn = 0;  // testing / tuning
+  float* splitk_ws = nullptr;  // split-K scratch: conv_splitk_plan(a).splits * pixels * N floats (null: no split-K)
   bool force_v1 = false;  // one-tile-per-CTA kernel (gemm.cuh) instead of the persistent one (gemm2.cuh)
 };
 
@@ -164,12 +165,99 @@ inline G3Plan plan_gemm3(int N, long long m_tiles, int act, int force_bn, int it
 }
 static constexpr size_t kSmemLimit = 232448;  // 227 KB per CTA on sm_100
 
+// ---- split-K ----
+// Layers with few output tiles and a long K loop (the 8x8 level at batch 16: 1024 pixels x 1280 channels, K = 9 x 1280
+// or 9 x 2560) fill 80 of 148 SMs, and each CTA is bound by L2->SM operand delivery (~46 B/clk/SM): 54 us for a conv
+// that is 20 us of tensor work.  Their k-iterations are cut into `splits` ranges, one unit each, with wide tiles
+// (BN 320 / 256: fewer operand bytes per FLOP); fp32 partial sums go to scratch and splitk_reduce_kernel adds them in
+// index order (deterministic) and applies the usual epilogue once.
+struct SplitKPlan {
+  int splits = 1, cg = 1, bn = 0, n_mma = 1, iters_split = 0;
+};
+inline int splitk_enabled() {
+  static int v = env_int("SDTF_SPLITK", 1);
+  return v;
+}
+inline SplitKPlan plan_splitk(int N, long long m_tiles, int iters, int act, bool bf16_out) {
+  SplitKPlan pl;
+  if (!splitk_enabled() || !bf16_out || (act != ACT_NONE && act != ACT_SILU) || iters < 60 || N % 8 != 0) return pl;
+  static const int cands[4] = {320, 256, 160, 128};
+  static const int force_bn = env_int("SDTF_SPLITK_BN", 0), max_splits = env_int("SDTF_SPLITK_MAX", 8);  // tuning
+  const int cg = m_tiles >= 2 ? 2 : 1;
+  const long long m_units = (m_tiles + cg - 1) / cg;
+  const long long slots = sm_count() / cg;
+  for (int bn : cands) {
+    if (N % bn || (force_bn && bn != force_bn)) continue;
+    const int n_mma = bn > 256 ? 2 : 1;
+    if ((bn / n_mma) % 16 != 0 || (cg == 2 && (bn / n_mma / 2) % 8 != 0)) continue;
+    const long long base = m_units * (N / bn);
+    if (base * 2 > slots) return pl;  // the plain schedule already covers more than half of the machine
+    int splits = (int)(slots / base);
+    if (splits > max_splits) splits = max_splits;
+    if (splits > iters / 16) splits = iters / 16;
+    if (splits < 2) return pl;
+    pl.iters_split = (iters + splits - 1) / splits;
+    pl.splits = (iters + pl.iters_split - 1) / pl.iters_split;
+    pl.cg = cg; pl.bn = bn; pl.n_mma = n_mma;
+    return pl;
+  }
+  return pl;
+}
+
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long M, int N, long long rows_per_b,
+                     const float* __restrict__ bias, const float* __restrict__ temb, int temb_ld, const bf16* __restrict__ res,
+                     long long res_ld, bf16* __restrict__ out, long long out_ld, int act, float out_scale) {
+  pdl_trigger();
+  pdl_wait();
+  const int nv = N >> 2;
+  const long long total = M * nv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / nv;
+    const int c = (int)(i - m * nv) << 2;
+    float4 a = __ldcs(reinterpret_cast<const float4*>(partial + m * N + c));
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldcs(reinterpret_cast<const float4*>(partial + ((long long)s * M + m) * N + c));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    a.x *= out_scale; a.y *= out_scale; a.z *= out_scale; a.w *= out_scale;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) v = __ldg(reinterpret_cast<const float4*>(bias + c));
+    if (temb) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(temb + (m / rows_per_b) * temb_ld + c));
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    if (res) {
+      const uint2 r = *reinterpret_cast<const uint2*>(res + m * res_ld + c);
+      const __nv_bfloat162 r0 = *reinterpret_cast<const __nv_bfloat162*>(&r.x), r1 = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+      a.x += __bfloat162float(r0.x); a.y += __bfloat162float(r0.y); a.z += __bfloat162float(r1.x); a.w += __bfloat162float(r1.y);
+    }
+    if (act == ACT_SILU) { a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w); }
+    uint2 o;
+    o.x = tc05::pack_bf16(a.x, a.y);
+    o.y = tc05::pack_bf16(a.z, a.w);
+    *reinterpret_cast<uint2*>(out + m * out_ld + c) = o;
+  }
+}
+
 // called once per process before any launch (and before any stream capture)
 inline void init_gemm_kernels() {
   SDTF_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   sm_count();
+}
+
+// floats of split-K scratch launch_conv would use for this conv (0: the layer is not split)
+inline size_t conv_splitk_floats(const ConvArgs& a) {
+  const PackedWeight& w = *a.w;
+  if (a.out_fp32 || a.force_v1 || a.force_bn || gemm_v1_forced()) return 0;
+  const TileShape ts = choose_tile(a.outW, a.outH, a.a0.B);
+  const long long m_tiles = (long long)ceil_div(a.outW, ts.bw) * ceil_div(a.outH, ts.bh) * ceil_div(a.a0.B, ts.bn);
+  const int iters = w.kh * w.kw * (ceil_div(a.a0.C, 64) + (a.a1.p ? ceil_div(a.a1.C, 64) : 0));
+  const SplitKPlan sk = plan_splitk(w.N, m_tiles, iters, a.act, true);
+  return sk.splits > 1 ? (size_t)sk.splits * a.a0.B * a.outH * a.outW * w.N : 0;
 }
 
 inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
@@ -205,7 +293,14 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   const bool aligned = Nout % 8 == 0 && a.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
                        (a.res == nullptr || (a.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0));
   if (!a.out_fp32 && !a.force_v1 && !gemm_v1_forced() && aligned) {
-    const G3Plan plan = plan_gemm3(w.N, m_tiles, a.act, a.force_bn, iters);
+    G3Plan plan = plan_gemm3(w.N, m_tiles, a.act, a.force_bn, iters);
+    SplitKPlan sk;
+    if (a.splitk_ws && !a.force_bn) sk = plan_splitk(w.N, m_tiles, iters, a.act, true);
+    const bool split = sk.splits > 1;
+    if (split) {  // partial sums only: bias / time embedding / residual / activation move to the reduce kernel
+      plan.cg = sk.cg; plan.bn = sk.bn; plan.n_mma = sk.n_mma; plan.bufs = sk.bn > 256 ? 1 : 2;
+      p.bias = nullptr; p.temb = nullptr; p.res = nullptr; p.act = ACT_NONE; p.out_scale = 1.f;
+    }
     p.BN = plan.bn;
     const int ncols = geglu ? p.BN / 2 : p.BN;
     const int n_tiles = ceil_div(w.N, p.BN);
@@ -229,17 +324,20 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       int lg = 0;
       while ((1 << lg) < p.bw * p.bh) ++lg;
       x.log_rows_per_b = lg;
-      x.vec_rows = a.temb ? p.bn : 1;
+      x.splits = split ? sk.splits : 1;
+      x.iters_split = split ? sk.iters_split : iters;
+      x.partial = split ? a.splitk_ws : nullptr;
+      x.vec_rows = (a.temb && !split) ? p.bn : 1;
       x.vec_width = ((geglu ? p.BN : ncols) + 31) / 32 * 32;
       const size_t vec_bytes = (size_t)2 * x.vec_rows * x.vec_width * 4;
       const int cg = plan.cg;
       const size_t stage_bytes = kATileBytes + (size_t)(p.BN / cg) * 128;
-      x.nbufs = a.res ? kG3MaxBufs : 4;  // residual tiles are TMA-prefetched nbufs-1 passes ahead: latency needs depth
+      x.nbufs = (a.res && !split) ? kG3MaxBufs : 4;  // residual tiles are TMA-prefetched nbufs-1 passes ahead: latency needs depth
       const int kG3Bufs = x.nbufs;
       const size_t fixed = 1024 + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * 10 + 4 + 2 * kG3Bufs) + 32 + vec_bytes;
       int st = (int)((kSmemLimit - fixed) / stage_bytes);
       if (st > 10) st = 10;
-      if (st > iters) st = iters < 2 ? 2 : iters;
+      if (st > x.iters_split) st = x.iters_split < 2 ? 2 : x.iters_split;
       SDTF_CHECK(st >= 2, "gemm3: tile does not fit shared memory");
       p.stages = st;
       const size_t smem = 1024 + (size_t)st * stage_bytes + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * st + 4 + 2 * kG3Bufs) + 32 + vec_bytes;
@@ -247,8 +345,8 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       CUtensorMap tmA1 = a.a1.p ? make_act_tmap(a.a1, p.bw, p.bh, p.bn, a.stride) : tmA0;
       CUtensorMap tmB = make_weight_tmap(w.w, w.K, w.N, p.taps, p.BN / plan.n_mma / cg);
       CUtensorMap tmOut = make_epi_tmap(reinterpret_cast<const bf16*>(a.out), Nout, p.W, p.H, p.B, a.out_ld, p.bw, p.bh, p.bn);
-      CUtensorMap tmRes = a.res ? make_epi_tmap(a.res, Nout, p.W, p.H, p.B, a.res_ld, p.bw, p.bh, p.bn) : tmOut;
-      const long long units = ((m_tiles + cg - 1) / cg) * n_tiles;
+      CUtensorMap tmRes = (a.res && !split) ? make_epi_tmap(a.res, Nout, p.W, p.H, p.B, a.res_ld, p.bw, p.bh, p.bn) : tmOut;
+      const long long units = ((m_tiles + cg - 1) / cg) * n_tiles * x.splits;
       const long long slots = sm_count() / cg;
       const unsigned grid = (unsigned)((units < slots ? units : slots) * cg);
       // SDTF_GEMM_PROFILE=1: per-role wait-cycle accounting, printed after the launch (debug; synchronises)
@@ -264,6 +362,14 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       if (cg == 2) launch_pdl(conv_gemm3_kernel<2>, dim3(grid), dim3(kG3Threads), smem, stream, 2, tmA0, tmA1, tmB, tmOut, tmRes, p, x);
       else launch_pdl(conv_gemm3_kernel<1>, dim3(grid), dim3(kG3Threads), smem, stream, 1, tmA0, tmA1, tmB, tmOut, tmRes, p, x);
       SDTF_CUDA(cudaGetLastError());
+      if (split) {
+        const long long M = (long long)p.B * p.H * p.W;
+        long long blocks = ceil_div_ll(M * (w.N / 4), 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        launch_pdl(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, (const float*)a.splitk_ws, x.splits, M, w.N,
+                   (long long)p.H * p.W, w.bias, a.temb, a.temb_ld, a.res, a.res_ld, reinterpret_cast<bf16*>(a.out), a.out_ld, a.act,
+                   a.out_scale);
+      }
       if (profile) {
         SDTF_CUDA(cudaStreamSynchronize(stream));
         std::vector<long long> h(16 * 160);
@@ -279,8 +385,8 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       }
       static const int verbose = env_int("SDTF_GEMM_VERBOSE", 0);
       if (verbose)
-        fprintf(stderr, "[gemm3] M-tiles %lld N %d K-iters %d -> CG %d BN %d (x%d MMA, %d acc) stages %d grid %u\n", m_tiles, w.N,
-                iters, cg, p.BN, plan.n_mma, plan.bufs, st, grid);
+        fprintf(stderr, "[gemm3] M-tiles %lld N %d K-iters %d -> CG %d BN %d (x%d MMA, %d acc) stages %d grid %u split-K %d\n", m_tiles, w.N,
+                iters, cg, p.BN, plan.n_mma, plan.bufs, st, grid, x.splits);
       return;
     }
   }

@@ -145,6 +145,10 @@ static bool run_case(const Case& c, bool bench) {
   a.w = &pw; a.stride = c.stride; a.pad_t = c.pad_t; a.pad_l = c.pad_l; a.outH = c.outH; a.outW = c.outW;
   a.temb = temb; a.temb_ld = Nout; a.res = res; a.res_ld = out_ld; a.out = out; a.out_ld = out_ld;
   a.out_fp32 = c.out_fp32; a.act = c.act; a.force_bn = c.force_bn;
+  // split-K scratch, exactly as the engine's launch context provides it (0 floats: the layer is not split)
+  const size_t skf = conv_splitk_floats(a);
+  float* skws = skf ? dalloc<float>(skf) : nullptr;
+  a.splitk_ws = skws;
 
   launch_conv(0, a);
   cudaError_t e = cudaDeviceSynchronize();
@@ -212,7 +216,7 @@ static bool run_case(const Case& c, bool bench) {
     double flop = 2.0 * opix * c.N * (double)K * taps;
     printf("BENCH %-27s  %.3f ms  %.1f TFLOP/s\n", c.name, ms, flop / ms * 1e-9);
   }
-  cudaFree(a0); cudaFree(a1); cudaFree(w); cudaFree(bias); cudaFree(temb); cudaFree(res); cudaFree(out); cudaFree(ref);
+  cudaFree(skws); cudaFree(a0); cudaFree(a1); cudaFree(w); cudaFree(bias); cudaFree(temb); cudaFree(res); cudaFree(out); cudaFree(ref);
   fflush(stdout);
   return ok;
 }
@@ -247,12 +251,20 @@ int main(int argc, char** argv) {
       {"linear_n1280_bn80_res",    1, 1, 1024, 1280,  0, 1280, 1, 1, 1, 0, 0, 1, 1024, true, false, true, false, ACT_NONE, 80, 0},
       {"linear_geglu_m1000",       1, 1, 1000, 640,   0, 5120, 1, 1, 1, 0, 0, 1, 1000, true, false, false, false, ACT_GEGLU, 0, 0},
       {"conv3x3_96ch_slice_res",   2, 32, 32,  96,  0,  96, 3, 3, 1, 1, 1, 32, 32, true, false, true, false, ACT_NONE, 0, 32},
+      // split-K (few tiles, long K): CTA pairs with BN 320, one-CTA units, concat K loop, residual, SiLU, strided view, stride 2
+      {"splitk_8x8_b16_1280_temb", 16, 8, 8, 1280,  0, 1280, 3, 3, 1, 1, 1, 8, 8, true, true, false, false, ACT_NONE, 0, 0},
+      {"splitk_8x8_b16_cat_res",   16, 8, 8, 1280, 1280, 1280, 3, 3, 1, 1, 1, 8, 8, true, false, true, false, ACT_NONE, 0, 0},
+      {"splitk_8x8_b2_silu",        2, 8, 8, 640,   0, 320, 3, 3, 1, 1, 1, 8, 8, true, false, false, false, ACT_SILU, 0, 0},
+      {"splitk_16x16_b2_res_ldx",   2, 16, 16, 1280, 0, 1280, 3, 3, 1, 1, 1, 16, 16, true, true, true, false, ACT_NONE, 0, 32},
+      {"splitk_s2_16to8_b16",      16, 16, 16, 1280, 0, 1280, 3, 3, 2, 1, 1, 8, 8, true, false, false, false, ACT_NONE, 0, 0},
+      {"splitk_3x5_b3_n640",        3, 3, 5, 1280,  0, 640, 3, 3, 1, 1, 1, 3, 5, true, false, true, false, ACT_NONE, 0, 0},
   };
   std::vector<Case> bench_cases = {
       {"b16_conv3x3_64_320",      16, 64, 64, 320,  0, 320, 3, 3, 1, 1, 1, 64, 64, true, true, false, false, ACT_NONE, 0, 0},
       {"b16_conv3x3_32_640",      16, 32, 32, 640,  0, 640, 3, 3, 1, 1, 1, 32, 32, true, true, false, false, ACT_NONE, 0, 0},
       {"b16_conv3x3_16_1280",     16, 16, 16, 1280, 0, 1280, 3, 3, 1, 1, 1, 16, 16, true, true, false, false, ACT_NONE, 0, 0},
       {"b16_conv3x3_8_1280",      16, 8, 8, 1280,   0, 1280, 3, 3, 1, 1, 1, 8, 8, true, true, false, false, ACT_NONE, 0, 0},
+      {"b16_conv3x3_8_2560cat",   16, 8, 8, 1280, 1280, 1280, 3, 3, 1, 1, 1, 8, 8, true, true, false, false, ACT_NONE, 0, 0},
       {"b16_conv3x3_64_960cat",   16, 64, 64, 640, 320, 320, 3, 3, 1, 1, 1, 64, 64, true, true, false, false, ACT_NONE, 0, 0},
       {"b16_geglu_4096x320",       1, 1, 65536, 320, 0, 2560, 1, 1, 1, 0, 0, 1, 65536, true, false, false, false, ACT_GEGLU, 0, 0},
       {"b16_ff2_4096x1280",        1, 1, 65536, 1280, 0, 320, 1, 1, 1, 0, 0, 1, 65536, true, false, true, false, ACT_NONE, 0, 0},
