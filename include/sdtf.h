@@ -134,6 +134,11 @@ int sdtf_vae_decode(sdtf_engine* e, const DLManagedTensor* latent, DLManagedTens
 /* ImageEncoder.predict_on_batch(image in [-1,1]) -> (B,H/8,W/8,4) f32 — image_encoder.py:21-48 */
 int sdtf_vae_encode(sdtf_engine* e, const DLManagedTensor* image, DLManagedTensor* out_latent);
 
+/* TextEncoder.predict_on_batch(TextClipEmbedding.predict_on_batch([tokens, positions])) — text_encoder.py:106-135:
+ * tokens (B,T<=77) int32 -> context (B,T,768) f32; clip_skip in [-12,-1] selects the encoder layer whose output is
+ * normalised (text_encoder.py:133).  Component "text_encoder", keys text_model.* (text_encoder.py:110-111,137-157). */
+int sdtf_text_encode(sdtf_engine* e, const DLManagedTensor* tokens, int clip_skip, DLManagedTensor* out_context);
+
 /* CFG combine + rescale + Scheduler.step (+ inpaint blend) as ONE kernel — stable_diffusion.py:458-475,
  * scheduler.py:246-315.  eps_u may be NULL (no guidance).  All (B,h,w,4) f32 except mask (h,w), init_latent (h,w,4). */
 int sdtf_cfg_sched_step(sdtf_engine* e, const DLManagedTensor* eps_u, const DLManagedTensor* eps_c,

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libsdtf.so")
 
 EXPORTS = [
     "sdtf_create", "sdtf_destroy", "sdtf_last_error", "sdtf_version", "sdtf_load_tensor", "sdtf_finalize_weights",
-    "sdtf_unet_forward", "sdtf_controlnet_forward", "sdtf_hintnet_forward", "sdtf_vae_decode", "sdtf_vae_encode",
+    "sdtf_unet_forward", "sdtf_controlnet_forward", "sdtf_hintnet_forward", "sdtf_vae_decode", "sdtf_vae_encode", "sdtf_text_encode",
     "sdtf_cfg_sched_step", "sdtf_to_uint8", "sdtf_denoise", "sdtf_get_timings", "sdtf_bench_conv", "sdtf_bench_attention",
     "sdtf_test_attention", "sdtf_test_norm", "sdtf_comm_unique_id", "sdtf_comm_init", "sdtf_comm_destroy",
 ]
@@ -70,6 +70,7 @@ def load():
     lib.sdtf_hintnet_forward.argtypes = [vp, vp, vp]
     lib.sdtf_vae_decode.argtypes = [vp, vp, vp]
     lib.sdtf_vae_encode.argtypes = [vp, vp, vp]
+    lib.sdtf_text_encode.argtypes = [vp, vp, i32, vp]
     lib.sdtf_cfg_sched_step.argtypes = [vp, vp, vp, vp, ctypes.POINTER(StepCoef), vp, vp, vp, vp, vp]
     lib.sdtf_to_uint8.argtypes = [vp, vp, vp, vp, vp]
     lib.sdtf_denoise.argtypes = [vp, ctypes.POINTER(DenoiseDesc)]

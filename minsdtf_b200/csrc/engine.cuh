@@ -94,9 +94,26 @@ inline int skip_mask() {
 // SDTF_TRACE=1 (debug, eager launches only): every operator is bracketed by CUDA events on the engine's stream and
 // one line per launch goes to stderr — kind, shape, microseconds, TFLOP/s and GB/s of algorithmic work — in graph order,
 // with the caches in the state the previous operator left them (unlike an ncu replay).  tools/trace_table.py sums it.
-inline bool trace_on() {
+inline int trace_level() {
   static const int v = getenv("SDTF_TRACE") ? atoi(getenv("SDTF_TRACE")) : 0;
-  return v != 0;
+  return v;
+}
+inline bool trace_on() { return trace_level() != 0; }
+
+// SDTF_TRACE=2 additionally prints an order-independent fingerprint (sum and xor of the bf16 bit patterns) of the LAST
+// sample of every operator output: two runs that should agree bit for bit (a sample alone vs inside a batch, graph vs
+// eager) can be diffed operator by operator (tools/batch_invariance.py).
+__global__ void fingerprint_kernel(const bf16* __restrict__ x, long long ld, int C, long long pixels, unsigned long long* out) {
+  unsigned long long s = 0, xo = 0;
+  const long long total = pixels * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / C;
+    const unsigned short b = *reinterpret_cast<const unsigned short*>(x + p * ld + (i - p * C));
+    s += b;
+    xo ^= (unsigned long long)b << ((i & 3) * 16);
+  }
+  atomicAdd(out, s);
+  atomicXor(out + 1, xo);
 }
 
 struct Ctx {
@@ -123,6 +140,23 @@ struct Ctx {
     SDTF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
     fprintf(stderr, "[trace] %-6s %-44s %9.2f us %8.1f TFLOP/s %8.1f GB/s\n", kind, shape.c_str(), ms * 1e3, flop / (ms * 1e9),
             bytes / (ms * 1e6));
+  }
+  // fingerprint of the last sample of an NHWC view (SDTF_TRACE=2, eager launches only)
+  void fingerprint(const char* kind, const bf16* p, long long ld, int C, long long pixels_per_sample, int B) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (trace_level() < 2 || dry || (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)) return;
+    static unsigned long long* d = nullptr;
+    if (!d) SDTF_CUDA(cudaMalloc((void**)&d, 16));
+    SDTF_CUDA(cudaMemsetAsync(d, 0, 16, st));
+    // token-shaped views fold the batch into the pixel count: SDTF_TRACE_BATCH tells how many samples the call carries
+    static const int tb = getenv("SDTF_TRACE_BATCH") ? atoi(getenv("SDTF_TRACE_BATCH")) : 0;
+    const long long total = pixels_per_sample * B;
+    if (tb > 0) { pixels_per_sample = total / tb; B = tb; }
+    fingerprint_kernel<<<64, 256, 0, st>>>(p + (long long)(B - 1) * pixels_per_sample * ld, ld, C, pixels_per_sample, d);
+    unsigned long long h[2];
+    SDTF_CUDA(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, st));
+    SDTF_CUDA(cudaStreamSynchronize(st));
+    fprintf(stderr, "[fp] %-6s C%-5d px%-6lld %016llx %016llx\n", kind, C, pixels_per_sample, h[0], h[1]);
   }
 
   View alloc_view(int B, int H, int W, int C) {
@@ -154,6 +188,7 @@ struct Ctx {
     traced("conv", buf, 2.0 * M * w.N * K * w.kh * w.kw,
            2.0 * ((double)a.a0.B * a.a0.H * a.a0.W * K + M * Nout * (a.res ? 2 : 1) + (double)w.N * K * w.kh * w.kw),
            [&] { launch_conv(st, a); });
+    if (!a.out_fp32) fingerprint("conv", reinterpret_cast<const bf16*>(a.out), a.out_ld, Nout, (long long)a.outH * a.outW, a.a0.B);
   }
   // y = conv(x) (+bias) (+temb) (+res) ; out view may be a channel slice
   void conv(const View& x, const PackedWeight& w, const View& out, int stride = 1, int pad = -1, const View* res = nullptr,
@@ -178,6 +213,7 @@ struct Ctx {
     char buf[64];
     snprintf(buf, sizeof buf, "%dx%dx%dx%d%s", x.B, x.H, x.W, x.C, silu ? " silu" : "");
     traced("gn", buf, 0.0, 4.0 * x.pixels() * x.C, [&] { launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn); });
+    fingerprint("gn", y.p, y.ld, x.C, (long long)x.H * x.W, x.B);
   }
   void layernorm(const View& x, const NormW& n, const View& y) {
     ++launches;

@@ -21,7 +21,7 @@
 
 namespace sdtf {
 
-enum : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2 };
+enum : int { ACT_NONE = 0, ACT_SILU = 1, ACT_GEGLU = 2, ACT_QGELU = 3 };  // QGELU: x * sigmoid(1.702 x) (CLIP text tower)
 
 struct GemmParams {
   // output pixel space [B][H][W] and the 128-pixel tile shape
@@ -55,6 +55,7 @@ static constexpr int kBK = 64;
 static constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float qgelu_f(float x) { return x / (1.f + __expf(-1.702f * x)); }
 // tanh-approximation GELU exactly as the reference spells it (diffusion_model.py:150-153)
 __device__ __forceinline__ float gelu_tanh_f(float g) {
   float u = g * 0.7978845608f * (1.f + 0.044715f * g * g);
@@ -244,6 +245,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant
     if (p.act == ACT_SILU) {
 #pragma unroll
       for (int i = 0; i < 16; ++i) f[i] = silu_f(f[i]);
+    }
+    if (p.act == ACT_QGELU) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = qgelu_f(f[i]);
     }
     if (p.out_fp32) {
       float* op = reinterpret_cast<float*>(p.out) + pix * p.out_ld + col;

@@ -477,6 +477,10 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
         }
+        if (p.act == ACT_QGELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = qgelu_f(f[i]);
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 o;

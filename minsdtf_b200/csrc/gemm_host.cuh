@@ -178,25 +178,23 @@ inline int splitk_enabled() {
   static int v = env_int("SDTF_SPLITK", 1);
   return v;
 }
-inline SplitKPlan plan_splitk(int N, long long m_tiles, int iters, int act, bool bf16_out) {
+// The decision and the K partition depend on the layer (output pixels per sample, N, K) and NEVER on the batch size: a
+// sample's result must not depend on what it is batched with (fp32 partial sums round differently from one
+// accumulator), see test_full_size_batching_and_determinism.  Rule: the 8x8 level and below (<= 64 output pixels per
+// sample), spatial filters only (the linears run on token-shaped views that fold the batch into the pixel count), at
+// least 60 k-iterations, 4 ranges.
+inline SplitKPlan plan_splitk(int N, long long m_tiles, int iters, int act, bool bf16_out, long long pixels_per_sample, int taps) {
   SplitKPlan pl;
   if (!splitk_enabled() || !bf16_out || (act != ACT_NONE && act != ACT_SILU) || iters < 60 || N % 8 != 0) return pl;
+  if (pixels_per_sample > 64 || taps == 1) return pl;
   static const int cands[4] = {320, 256, 160, 128};
-  static const int force_bn = env_int("SDTF_SPLITK_BN", 0), max_splits = env_int("SDTF_SPLITK_MAX", 8);  // tuning
+  static const int force_bn = env_int("SDTF_SPLITK_BN", 0), n_splits = env_int("SDTF_SPLITK_N", 4);  // tuning
   const int cg = m_tiles >= 2 ? 2 : 1;
-  const long long m_units = (m_tiles + cg - 1) / cg;
-  const long long slots = sm_count() / cg;
   for (int bn : cands) {
     if (N % bn || (force_bn && bn != force_bn)) continue;
     const int n_mma = bn > 256 ? 2 : 1;
     if ((bn / n_mma) % 16 != 0 || (cg == 2 && (bn / n_mma / 2) % 8 != 0)) continue;
-    const long long base = m_units * (N / bn);
-    if (base * 2 > slots) return pl;  // the plain schedule already covers more than half of the machine
-    int splits = (int)(slots / base);
-    if (splits > max_splits) splits = max_splits;
-    if (splits > iters / 16) splits = iters / 16;
-    if (splits < 2) return pl;
-    pl.iters_split = (iters + splits - 1) / splits;
+    pl.iters_split = (iters + n_splits - 1) / n_splits;
     pl.splits = (iters + pl.iters_split - 1) / pl.iters_split;
     pl.cg = cg; pl.bn = bn; pl.n_mma = n_mma;
     return pl;
@@ -256,7 +254,7 @@ inline size_t conv_splitk_floats(const ConvArgs& a) {
   const TileShape ts = choose_tile(a.outW, a.outH, a.a0.B);
   const long long m_tiles = (long long)ceil_div(a.outW, ts.bw) * ceil_div(a.outH, ts.bh) * ceil_div(a.a0.B, ts.bn);
   const int iters = w.kh * w.kw * (ceil_div(a.a0.C, 64) + (a.a1.p ? ceil_div(a.a1.C, 64) : 0));
-  const SplitKPlan sk = plan_splitk(w.N, m_tiles, iters, a.act, true);
+  const SplitKPlan sk = plan_splitk(w.N, m_tiles, iters, a.act, true, (long long)a.outH * a.outW, w.kh * w.kw);
   return sk.splits > 1 ? (size_t)sk.splits * a.a0.B * a.outH * a.outW * w.N : 0;
 }
 
@@ -295,20 +293,20 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   if (!a.out_fp32 && !a.force_v1 && !gemm_v1_forced() && aligned) {
     G3Plan plan = plan_gemm3(w.N, m_tiles, a.act, a.force_bn, iters);
     SplitKPlan sk;
-    if (a.splitk_ws && !a.force_bn) sk = plan_splitk(w.N, m_tiles, iters, a.act, true);
+    if (a.splitk_ws && !a.force_bn) sk = plan_splitk(w.N, m_tiles, iters, a.act, true, (long long)a.outH * a.outW, w.kh * w.kw);
     const bool split = sk.splits > 1;
-    if (split) {  // partial sums only: bias / time embedding / residual / activation move to the reduce kernel
-      plan.cg = sk.cg; plan.bn = sk.bn; plan.n_mma = sk.n_mma; plan.bufs = sk.bn > 256 ? 1 : 2;
-      p.bias = nullptr; p.temb = nullptr; p.res = nullptr; p.act = ACT_NONE; p.out_scale = 1.f;
-    }
+    if (split) { plan.cg = sk.cg; plan.bn = sk.bn; plan.n_mma = sk.n_mma; plan.bufs = sk.bn > 256 ? 1 : 2; }
     p.BN = plan.bn;
     const int ncols = geglu ? p.BN / 2 : p.BN;
     const int n_tiles = ceil_div(w.N, p.BN);
     // a last pass narrower than 32 columns is shifted back over columns the tile already wrote: fine unless the
     // residual is read from the tensor being written
     const bool overlap_ok = ncols % 32 == 0 || ncols < 32 || a.res != a.out;
-    const bool vec_ok = a.temb == nullptr || p.bn <= 4;  // the staged epilogue vector holds up to 4 sample rows
+    const bool vec_ok = split || a.temb == nullptr || p.bn <= 4;  // the staged epilogue vector holds up to 4 sample rows
     if (vec_ok && (ncols % 32 == 0 || (ncols < 32 && n_tiles == 1) || (ncols > 32 && overlap_ok))) {
+      if (split) {  // partial sums only: bias / time embedding / residual / activation move to the reduce kernel
+        p.bias = nullptr; p.temb = nullptr; p.res = nullptr; p.act = ACT_NONE; p.out_scale = 1.f;
+      }
       if (geglu) SDTF_CHECK(w.geglu_half * 2 == p.BN && w.N % p.BN == 0, "GEGLU weight packing must match BN");
       Gemm3Extra x{};
       x.m_tiles = (int)m_tiles;

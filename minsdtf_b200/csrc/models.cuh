@@ -635,4 +635,96 @@ inline void vae_encode(Ctx& c, const VaeEncW& e, const float* image, int B, int 
   c.ws->release(m0);
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// CLIP text tower (reference: text_encoder.py:22-33 embeddings, :36-55 encoder layer,
+// :58-99 attention, :102-103 quick-GELU, :125-135 TextEncoder with clip_skip).  12 layers x (LN, q|k|v, causal
+// attention, out + residual, LN, fc1 + quick-GELU, fc2 + residual), final LayerNorm of layer output `clip_skip`.
+// The linears run on the same persistent tcgen05 GEMM as the UNet (M = B * 77 token rows).
+// ----------------------------------------------------------------------------------------------------------
+static constexpr int kClipLayers = 12, kClipHeads = 12, kClipTokens = 77;
+
+struct TextLayerW {
+  NormW ln1, ln2;
+  PackedWeight qkv, out, fc1, fc2;
+};
+struct TextW {
+  float* tok = nullptr;  // [vocab][768] fp32
+  float* pos = nullptr;  // [77][768]
+  int vocab = 0, max_len = 0;
+  TextLayerW layer[kClipLayers];
+  NormW final_ln;
+  bool ready = false;
+};
+
+inline void build_text_encoder(WeightStore& ws, TextW& t) {
+  const RawTensor* te = ws.find("text_model.embeddings.token_embedding.weight");
+  const RawTensor* pe = ws.find("text_model.embeddings.position_embedding.weight");
+  if (te && pe) {
+    t.vocab = (int)te->shape[0];
+    t.max_len = (int)pe->shape[0];
+    t.tok = ws.pack_vec(*te, nullptr, 1.f);
+    t.pos = ws.pack_vec(*pe, nullptr, 1.f);
+  }
+  const float qscale = 0.125f;  // head_dim^-1/2 = 64^-1/2, applied to q AFTER its bias in the reference (:84): folded into both
+  for (int l = 0; l < kClipLayers; ++l) {
+    const std::string p = "text_model.encoder.layers." + std::to_string(l);
+    TextLayerW& L = t.layer[l];
+    L.ln1 = ws.norm(p + ".layer_norm1");
+    L.ln2 = ws.norm(p + ".layer_norm2");
+    const RawTensor* w[3] = {ws.find(p + ".self_attn.q_proj.weight"), ws.find(p + ".self_attn.k_proj.weight"),
+                             ws.find(p + ".self_attn.v_proj.weight")};
+    const RawTensor* b[3] = {ws.find(p + ".self_attn.q_proj.bias"), ws.find(p + ".self_attn.k_proj.bias"),
+                             ws.find(p + ".self_attn.v_proj.bias")};
+    if (w[0] && w[1] && w[2] && b[0] && b[1] && b[2]) {
+      const int C = (int)w[0]->shape[1];
+      L.qkv.N = 3 * C; L.qkv.K = C; L.qkv.kh = L.qkv.kw = 1;
+      L.qkv.w = (bf16*)ws.pool.alloc((size_t)3 * C * C * 2);
+      L.qkv.bias = (float*)ws.pool.alloc((size_t)3 * C * 4);
+      for (int i = 0; i < 3; ++i) {
+        ws.pack_into(L.qkv.w, 3 * C, C, i * C, 0, *w[i], nullptr, i == 0 ? qscale : 1.f);
+        ws.pack_vec(*b[i], nullptr, i == 0 ? qscale : 1.f, L.qkv.bias, i * C);
+      }
+    }
+    L.out = ws.conv(p + ".self_attn.out_proj");
+    L.fc1 = ws.conv(p + ".mlp.fc1");
+    L.fc2 = ws.conv(p + ".mlp.fc2");
+  }
+  t.final_ln = ws.norm("text_model.final_layer_norm");
+}
+
+// tokens: [B][T] int32 on the device; out: [B][T][768] fp32.  clip_skip = -1: all 12 layers, -2: 11, ... (reference
+// indexing out[clip_skip], text_encoder.py:133)
+inline void text_encode(Ctx& c, const TextW& t, const int* tokens, int B, int T, int clip_skip, float* out) {
+  const int C = kCtxDim;
+  const int n_layers = kClipLayers + clip_skip + 1;
+  const size_t m0 = c.ws->mark();
+  const long long rows = (long long)B * T;
+  View x = c.alloc_view(1, 1, (int)rows, C), h = c.alloc_view(1, 1, (int)rows, C), a = c.alloc_view(1, 1, (int)rows, C);
+  View qkv = c.alloc_view(1, 1, (int)rows, 3 * C), f = c.alloc_view(1, 1, (int)rows, 4 * C);
+  ++c.launches;
+  if (!c.dry) {
+    long long blocks = ceil_div_ll(rows * (C / 4), 256);
+    clip_embed_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(tokens, t.tok, t.pos, t.vocab, T, C, rows, x.p);
+    SDTF_CUDA(cudaGetLastError());
+  }
+  for (int l = 0; l < n_layers; ++l) {
+    const TextLayerW& L = t.layer[l];
+    c.layernorm(x, L.ln1, h);
+    c.conv(h, L.qkv, qkv);
+    ++c.launches;
+    if (!c.dry) {
+      const size_t smem = ((size_t)2 * T * 65 + 4 * 128) * sizeof(float);
+      clip_causal_attn_kernel<<<dim3(kClipHeads, B), 128, smem, c.st>>>(qkv.p, T, C, a.p);
+      SDTF_CUDA(cudaGetLastError());
+    }
+    c.conv(a, L.out, x, 1, -1, &x);
+    c.layernorm(x, L.ln2, h);
+    c.conv(h, L.fc1, f, 1, -1, nullptr, nullptr, 0, ACT_QGELU);
+    c.conv(f, L.fc2, x, 1, -1, &x);
+  }
+  c.layernorm(x, t.final_ln, h);
+  c.cast_out(h.p, C, rows, C, out);
+  c.ws->release(m0);
+}
+
 }  // namespace sdtf

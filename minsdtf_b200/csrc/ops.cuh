@@ -519,6 +519,91 @@ inline void launch_skinny_linear(cudaStream_t st, const float* x, int M, int K, 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// CLIP text tower pieces (reference: text_encoder.py:22-33 CLIPEmbedding, :58-99 CLIPAttention).  Once per prompt, 77
+// tokens: latency-bound, plain CUDA.
+// ------------------------------------------------------------------------------------------------------
+// x[b][t][:] = token_embedding[tokens[b][t]] + position_embedding[t]  -> bf16
+__global__ void clip_embed_kernel(const int* __restrict__ tokens, const float* __restrict__ tok_emb, const float* __restrict__ pos_emb,
+                                  int vocab, int T, int C, long long rows, bf16* __restrict__ out) {
+  const long long total = rows * (C >> 2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (C >> 2);
+    const int c = (int)(i - r * (C >> 2)) << 2;
+    int tok = tokens[r];
+    tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(tok_emb + (long long)tok * C + c));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(pos_emb + (long long)(r % T) * C + c));
+    uint2 o;
+    o.x = tc05::pack_bf16(a.x + b.x, a.y + b.y);
+    o.y = tc05::pack_bf16(a.z + b.z, a.w + b.w);
+    *reinterpret_cast<uint2*>(out + r * C + c) = o;
+  }
+}
+
+// causal self-attention over T <= 128 tokens, head size 64: one CTA per (head, sample), a warp per query row.
+// qkv: [B*T][3*C] bf16 (q | k | v, q already scaled by d^-1/2 through its weights), out: [B*T][C] bf16
+__global__ void __launch_bounds__(128)
+clip_causal_attn_kernel(const bf16* __restrict__ qkv, int T, int C, bf16* __restrict__ out) {
+  constexpr int D = 64, LD = D + 1;
+  extern __shared__ float ca_sm[];  // K [T][65], V [T][65], P [4 warps][128]
+  float* sK = ca_sm;
+  float* sV = sK + T * LD;
+  float* sP = sV + T * LD;
+  const int head = blockIdx.x, b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* base = qkv + (long long)b * T * 3 * C + head * D;
+  for (int i = threadIdx.x; i < T * D; i += blockDim.x) {
+    const int t = i / D, d = i - t * D;
+    sK[t * LD + d] = __bfloat162float(base[(long long)t * 3 * C + C + d]);
+    sV[t * LD + d] = __bfloat162float(base[(long long)t * 3 * C + 2 * C + d]);
+  }
+  __syncthreads();
+  float* myP = sP + warp * 128;
+  for (int q = warp; q < T; q += 4) {
+    const float q0 = __bfloat162float(base[(long long)q * 3 * C + lane]);
+    const float q1 = __bfloat162float(base[(long long)q * 3 * C + 32 + lane]);
+    float sc[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = lane + 32 * k;
+      const int jj = j < T ? j : T - 1;  // every lane runs the same shuffles; masked keys are discarded below
+      float acc = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < 32; ++d) {
+        acc = fmaf(__shfl_sync(0xffffffffu, q0, d), sK[jj * LD + d], acc);
+        acc = fmaf(__shfl_sync(0xffffffffu, q1, d), sK[jj * LD + 32 + d], acc);
+      }
+      if (j > q) acc = -INFINITY;  // causal mask (text_encoder.py:78-81: -inf above the diagonal)
+      sc[k] = acc;
+      mx = fmaxf(mx, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float e = sc[k] == -INFINITY ? 0.f : __expf(sc[k] - mx);
+      myP[lane + 32 * k] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j <= q; ++j) {
+      const float pj = myP[j];
+      o0 = fmaf(pj, sV[j * LD + lane], o0);
+      o1 = fmaf(pj, sV[j * LD + 32 + lane], o1);
+    }
+    const float inv = 1.f / sum;
+    bf16* orow = out + ((long long)b * T + q) * C + head * D;
+    orow[lane] = __float2bfloat16(o0 * inv);
+    orow[32 + lane] = __float2bfloat16(o1 * inv);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // Fused CFG combine + CFG-rescale + scheduler update (+ inpaint blend)  — one CTA per sample.
 //   reference: stable_diffusion.py:458 (combine), :304-315 (rescale_noise_cfg, population std over h,w,c),
 //   scheduler.py:285-312 (DDIM / TCD update, coefficients pre-combined on the host in fp64),

@@ -101,6 +101,7 @@ struct sdtf_engine {
   ControlNetW cnet;
   VaeDecW vdec;
   VaeEncW venc;
+  TextW text;
   Arena ws;
   GnScratch gn;
   int* step_dev = nullptr;
@@ -307,8 +308,13 @@ int sdtf_finalize_weights(sdtf_engine* e, const char* component) {
     build_vae_encoder(w, e->venc);
     e->venc.ready = w.missing.empty();
     prefixes = {"encoder.", "quant_conv."};
+  } else if (comp == "text_encoder") {
+    e->text = TextW();
+    build_text_encoder(w, e->text);
+    e->text.ready = w.missing.empty();
+    prefixes = {"text_model."};
   } else {
-    throw Error("unknown component '" + comp + "' (unet | controlnet | vae_decoder | vae_encoder)");
+    throw Error("unknown component '" + comp + "' (unet | controlnet | vae_decoder | vae_encoder | text_encoder)");
   }
   SDTF_CUDA(cudaStreamSynchronize(e->st));
   if (!w.missing.empty()) {
@@ -458,6 +464,28 @@ int sdtf_vae_decode(sdtf_engine* e, const DLManagedTensor* latent, DLManagedTens
     float* img = c.ws->alloc_n<float>((size_t)out.numel());
     vae_decode(c, e->vdec, latf, B, h, w, img);
     e->emit(c, img, out);
+  });
+  SDTF_CUDA(cudaStreamSynchronize(e->st));
+  SDTF_API_END
+}
+
+int sdtf_text_encode(sdtf_engine* e, const DLManagedTensor* tokens, int clip_skip, DLManagedTensor* out_context) {
+  SDTF_API_BEGIN
+  SDTF_CHECK(e->text.ready, "text_encoder weights not finalized");
+  TRef tok = parse(tokens, "tokens", e->device), out = parse(out_context, "out_context", e->device);
+  SDTF_CHECK(tok.dt == I32, "tokens must be int32");
+  expect_shape(tok, {-1, -1}, "tokens");
+  const int B = (int)tok.shape[0], T = (int)tok.shape[1];
+  SDTF_CHECK(T >= 1 && T <= e->text.max_len, "tokens: sequence longer than the position table");
+  SDTF_CHECK(clip_skip <= -1 && clip_skip >= -kClipLayers, "clip_skip must be in [-12, -1]");
+  expect_shape(out, {B, T, kCtxDim}, "out_context");
+  SDTF_CHECK(out.dt == F32, "out_context must be float32");
+  e->run_sized([&](Ctx& c) {
+    int* d_tok = c.ws->alloc_n<int>((size_t)B * T);
+    if (!c.dry) SDTF_CUDA(cudaMemcpyAsync(d_tok, tok.data, tok.bytes(), tok.cuda ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->st));
+    float* ctx = c.ws->alloc_n<float>((size_t)out.numel());
+    text_encode(c, e->text, d_tok, B, T, clip_skip, ctx);
+    e->emit(c, ctx, out);
   });
   SDTF_CUDA(cudaStreamSynchronize(e->st));
   SDTF_API_END

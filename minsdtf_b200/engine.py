@@ -55,10 +55,11 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------------ weights
     def load_state_dict(self, sd: dict, component: str):
-        """component: 'unet' | 'controlnet' | 'vae_decoder' | 'vae_encoder'.  `sd` maps reference checkpoint keys
+        """component: 'unet' | 'controlnet' | 'vae_decoder' | 'vae_encoder' | 'text_encoder'.  `sd` maps reference checkpoint keys
         (or, for the UNet, their diffusers aliases — ckpt_loader.py:2160-2166) to tensors in PyTorch layout."""
         gens = {"unet": [K.unet_keys], "controlnet": [K.controlnet_keys, K.hintnet_keys],
-                "vae_decoder": [K.vae_decoder_keys], "vae_encoder": [K.vae_encoder_keys]}[component]
+                "vae_decoder": [K.vae_decoder_keys], "vae_encoder": [K.vae_encoder_keys],
+                "text_encoder": [K.text_encoder_keys]}[component]
         wanted = {}
         for g in gens:
             wanted.update(g())
@@ -167,6 +168,17 @@ class Engine:
         out = self._like(image, (B, H // 8, W // 8, 4))
         dl = _lib.DL()
         self._check(self._lib.sdtf_vae_encode(self._h, dl(image), dl(out)))
+        return out
+
+    def text_encode(self, tokens, clip_skip: int = -1):
+        """TextEncoder(TextClipEmbedding([tokens, positions])) (text_encoder.py:106-135): int tokens (B,T<=77) ->
+        context (B,T,768) float32 (NumPy)."""
+        tokens = np.ascontiguousarray(np.asarray(tokens, dtype=np.int32))
+        if tokens.ndim == 1:
+            tokens = tokens[None]
+        out = np.empty(tokens.shape + (768,), np.float32)
+        dl = _lib.DL()
+        self._check(self._lib.sdtf_text_encode(self._h, dl(tokens), int(clip_skip), dl(out)))
         return out
 
     def cfg_sched_step(self, eps_u, eps_c, latent_prev, coef, noise=None, mask=None, init_latent=None, init_noise=None):

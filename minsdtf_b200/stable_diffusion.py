@@ -79,16 +79,37 @@ class StableDiffusionBase:
                                    guidance_rescale=guidance_rescale, callback=callback)
 
     def encode_text(self, prompt, embedding_data=None):
-        """Reference: tokenizer + CLIP tower (:176-215).  Here: an ndarray is taken as already-encoded text; a string
-        needs `text_encoder_fn(prompt) -> (T,768)` (the text tower is the next item on the scope list)."""
-        if isinstance(prompt, np.ndarray):
+        """Reference: tokenizer -> TextClipEmbedding -> TextEncoder (:176-215).  Accepted here:
+        * a float array (T,768) / (B,T,768): already-encoded text, passed through;
+        * an integer array of CLIP token ids (T,) / (B,T<=77): encoded by the engine's text tower (`clip_skip` as given
+          to the constructor);
+        * a string: tokenised by `model.tokenizer` (any object with `.encode(str) -> ids`; the BPE vocabulary is a
+          download in the reference, clip_tokenizer.py:79-82, and is not available offline), padded with 49407 to 77.
+        Long-prompt weighting and textual-inversion embeddings (`embedding_data`) are host-side features outside the
+        hot path."""
+        if embedding_data is not None:
+            raise NotImplementedError("textual-inversion embeddings are outside the hot path (SURVEY.md §2)")
+        if isinstance(prompt, np.ndarray) and np.issubdtype(prompt.dtype, np.floating):
             return prompt.astype(np.float32)
-        fn = getattr(self, "text_encoder_fn", None)
-        if fn is None:
-            raise NotImplementedError(
-                "the CLIP text encoder / tokenizer is outside this round's scope (SURVEY.md §8f): pass an encoded "
-                "(T,768) array as `prompt`, call generate_image(encoded_text, ...), or set `model.text_encoder_fn`")
-        return np.asarray(fn(prompt), dtype=np.float32)
+        if isinstance(prompt, str):
+            tok = getattr(self, "tokenizer", None)
+            if tok is None:
+                fn = getattr(self, "text_encoder_fn", None)
+                if fn is not None:
+                    return np.asarray(fn(prompt), dtype=np.float32)
+                raise NotImplementedError(
+                    "no tokenizer: the CLIP BPE vocabulary cannot be downloaded offline — set `model.tokenizer` (an object with "
+                    ".encode(str) -> token ids), or pass token ids / an encoded (T,768) array as `prompt`")
+            ids = list(tok.encode(prompt))[:MAX_PROMPT_LENGTH]
+            ids = ids + [49407] * (MAX_PROMPT_LENGTH - len(ids))
+            prompt = np.asarray(ids, np.int32)
+        tokens = np.asarray(prompt)
+        if not np.issubdtype(tokens.dtype, np.integer):
+            raise TypeError("encode_text: expected a string, integer token ids or an encoded float array")
+        return self._encode_tokens(tokens)
+
+    def _encode_tokens(self, tokens):
+        raise NotImplementedError("token ids need the engine-backed StableDiffusion class")
 
     # ---------------------------------------------------------------------------------- host-side preprocessing
     def gaussian_blur(self, image, radius=3, h_axis=1, v_axis=2):
@@ -229,10 +250,10 @@ class StableDiffusionBase:
         ctx = getattr(self, "unconditional_context", None)
         if ctx is None:
             fn = getattr(self, "text_encoder_fn", None)
-            if fn is None:
-                raise NotImplementedError("set `model.unconditional_context` ((1,77,768) array) or `model.text_encoder_fn`; "
-                                          "the CLIP text tower is outside this round's scope")
-            ctx = np.asarray(fn(""), np.float32)
+            if fn is not None:
+                ctx = np.asarray(fn(""), np.float32)
+            else:  # the empty prompt: <start> then <end> padding (stable_diffusion.py:533-541, clip_tokenizer.py)
+                ctx = self._encode_tokens(np.asarray([[49406] + [49407] * (MAX_PROMPT_LENGTH - 1)], np.int32))
         ctx = np.asarray(ctx, np.float32)
         return ctx[None] if ctx.ndim == 2 else ctx
 
@@ -303,6 +324,7 @@ class StableDiffusion(StableDiffusionBase):
             from . import synth
             src = {"unet": lambda: synth.make_state_dict("unet"), "vae_decoder": lambda: synth.make_state_dict("decoder"),
                    "vae_encoder": lambda: synth.make_state_dict("encoder"),
+                   "text_encoder": lambda: synth.make_state_dict("text_encoder"),
                    "controlnet": synth.make_controlnet_state_dict}[component]()
         if isinstance(src, (str, os.PathLike)):
             eng.load_file(str(src), component)
@@ -343,13 +365,25 @@ class StableDiffusion(StableDiffusionBase):
         self._ensure("controlnet", self.controlnet_path)
         return _Model(lambda x: self.engine.controlnet(x[0], x[1], x[2], x[3]))
 
-    @property
-    def text_encoder(self):
-        raise NotImplementedError("CLIP text tower: next on the scope list (SURVEY.md §8f)")
-
+    # The reference splits the text tower into two Keras models, TextClipEmbedding([tokens, positions]) -> (B,77,768)
+    # and TextEncoder(embedding) (:700-725); the engine runs embedding lookup and the 12 layers in one call, so the
+    # first shim only carries the token ids to the second (the pair composes exactly like the reference's:
+    # `text_encoder.predict_on_batch(text_clip_embedding.predict_on_batch([tokens, positions]))`).
     @property
     def text_clip_embedding(self):
-        raise NotImplementedError("CLIP text tower: next on the scope list (SURVEY.md §8f)")
+        self._ensure("text_encoder", self.text_encoder_ckpt)
+        return _Model(lambda x: np.asarray(x[0], np.int32))
+
+    @property
+    def text_encoder(self):
+        self._ensure("text_encoder", self.text_encoder_ckpt)
+        return _Model(lambda tokens: self.engine.text_encode(tokens, self.clip_skip))
+
+    def _encode_tokens(self, tokens):
+        self._ensure("text_encoder", self.text_encoder_ckpt)
+        tokens = np.asarray(tokens, np.int32)
+        out = self.engine.text_encode(tokens, self.clip_skip)
+        return out[0] if tokens.ndim == 1 else out
 
     def generate_image(self, encoded_text, **kw):
         self._ensure("unet", self.unet_ckpt)

@@ -19,7 +19,7 @@ import torch
 from . import keys as K
 
 _HALF_GAIN = ("out_layers.3.weight", "to_out.0.weight", "ff.net.2.weight", "proj_out.weight", "zero_convs",
-              "middle_block_out", ".conv2.weight", "proj_attn.weight")
+              "middle_block_out", ".conv2.weight", "proj_attn.weight", "out_proj.weight", "mlp.fc2.weight")
 
 
 def _tensor(key: str, shape, seed: int) -> torch.Tensor:
@@ -36,8 +36,20 @@ def _tensor(key: str, shape, seed: int) -> torch.Tensor:
 
 
 def make_state_dict(component: str, seed: int = 123456) -> dict:
-    """component in {'unet','controlnet','hintnet','decoder','encoder'} -> {key: fp32 tensor (PyTorch layout)}."""
+    """component in {'unet','controlnet','hintnet','decoder','encoder','text_encoder'} -> {key: fp32 tensor (PyTorch layout)}."""
     return {k: _tensor(k, shp, seed) for k, shp in K.COMPONENT_KEYS[component]().items()}
+
+
+def prompt_tokens(batch, length=77, seed=123461):
+    """synthetic CLIP token ids (no tokenizer vocabulary offline): <start>, random word ids, <end> padding, as the
+    reference tokenizer pads (clip_tokenizer.py: start 49406, end / pad 49407)."""
+    rng = np.random.default_rng(seed)
+    out = np.full((batch, length), 49407, np.int32)
+    out[:, 0] = 49406
+    for b in range(batch):
+        n = int(rng.integers(3, length - 2))
+        out[b, 1:1 + n] = rng.integers(0, 49406, n)
+    return out
 
 
 def make_vae_state_dict(seed: int = 123456) -> dict:

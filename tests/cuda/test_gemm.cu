@@ -221,6 +221,64 @@ static bool run_case(const Case& c, bool bench) {
   return ok;
 }
 
+// A sample's conv result must not depend on what it is batched with: run a split-K layer on B samples, then on the
+// last sample alone (same device data), and compare bit for bit.
+static bool check_batch_invariance(int B, int HW, int C, int N, bool temb, bool res) {
+  const long long pix = (long long)B * HW * HW;
+  std::vector<float> h(pix * C);
+  for (auto& x : h) x = frand();
+  bf16* a0 = upload_bf16(h);
+  const int taps = 9;
+  h.assign((size_t)taps * N * C, 0.f);
+  for (auto& x : h) x = frand() * 0.01f;
+  bf16* w = upload_bf16(h);
+  h.resize(N);
+  for (auto& x : h) x = frand();
+  float* bias = upload_f32(h);
+  h.resize((size_t)B * N);
+  for (auto& x : h) x = frand();
+  float* te = upload_f32(h);
+  h.resize(pix * N);
+  for (auto& x : h) x = frand();
+  bf16* rs = upload_bf16(h);
+  bf16* out_all = dalloc<bf16>(pix * N);
+  bf16* out_one = dalloc<bf16>((long long)HW * HW * N);
+  PackedWeight pw;
+  pw.w = w; pw.bias = bias; pw.K = C; pw.N = N; pw.kh = 3; pw.kw = 3;
+  auto run = [&](int b0, int nb, bf16* out) {
+    ConvArgs a;
+    a.a0 = View{a0 + (long long)b0 * HW * HW * C, nb, HW, HW, C, C};
+    a.w = &pw; a.stride = 1; a.pad_t = 1; a.pad_l = 1; a.outH = HW; a.outW = HW;
+    if (temb) { a.temb = te + (long long)b0 * N; a.temb_ld = N; }
+    if (res) { a.res = rs + (long long)b0 * HW * HW * N; a.res_ld = N; }
+    a.out = out; a.out_ld = N;
+    const size_t skf = conv_splitk_floats(a);
+    float* ws = skf ? dalloc<float>(skf) : nullptr;
+    a.splitk_ws = ws;
+    launch_conv(0, a);
+    SDTF_CUDA(cudaDeviceSynchronize());
+    cudaFree(ws);
+    return skf;
+  };
+  const size_t f_all = run(0, B, out_all);
+  const size_t f_one = run(B - 1, 1, out_one);
+  const size_t n = (size_t)HW * HW * N;
+  std::vector<bf16> ha(n), ho(n);
+  SDTF_CUDA(cudaMemcpy(ha.data(), out_all + (long long)(B - 1) * n, n * 2, cudaMemcpyDeviceToHost));
+  SDTF_CUDA(cudaMemcpy(ho.data(), out_one, n * 2, cudaMemcpyDeviceToHost));
+  long long diff = 0;
+  double maxd = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const double d = fabs((double)__bfloat162float(ha[i]) - (double)__bfloat162float(ho[i]));
+    if (d != 0) ++diff;
+    if (d > maxd) maxd = d;
+  }
+  printf("CASE batch_invariance B%d %dx%d %d->%d%s%s  %s  split scratch %zu / %zu floats, %lld elements differ (max %.4g)\n", B, HW, HW, C, N,
+         temb ? " temb" : "", res ? " res" : "", diff == 0 ? "OK  " : "FAIL", f_all, f_one, diff, maxd);
+  cudaFree(a0); cudaFree(w); cudaFree(bias); cudaFree(te); cudaFree(rs); cudaFree(out_all); cudaFree(out_one);
+  return diff == 0;
+}
+
 int main(int argc, char** argv) {
   bool bench = argc > 1 && !strcmp(argv[1], "bench");
   const char* only = argc > 2 ? argv[2] : nullptr;  // bench <substr>: run only the benchmark cases whose name contains substr
@@ -255,7 +313,7 @@ int main(int argc, char** argv) {
       {"splitk_8x8_b16_1280_temb", 16, 8, 8, 1280,  0, 1280, 3, 3, 1, 1, 1, 8, 8, true, true, false, false, ACT_NONE, 0, 0},
       {"splitk_8x8_b16_cat_res",   16, 8, 8, 1280, 1280, 1280, 3, 3, 1, 1, 1, 8, 8, true, false, true, false, ACT_NONE, 0, 0},
       {"splitk_8x8_b2_silu",        2, 8, 8, 640,   0, 320, 3, 3, 1, 1, 1, 8, 8, true, false, false, false, ACT_SILU, 0, 0},
-      {"splitk_16x16_b2_res_ldx",   2, 16, 16, 1280, 0, 1280, 3, 3, 1, 1, 1, 16, 16, true, true, true, false, ACT_NONE, 0, 32},
+      {"splitk_4x4_b5_res_ldx",     5, 4, 4, 1280, 0, 1280, 3, 3, 1, 1, 1, 4, 4, true, true, true, false, ACT_NONE, 0, 32},
       {"splitk_s2_16to8_b16",      16, 16, 16, 1280, 0, 1280, 3, 3, 2, 1, 1, 8, 8, true, false, false, false, ACT_NONE, 0, 0},
       {"splitk_3x5_b3_n640",        3, 3, 5, 1280,  0, 640, 3, 3, 1, 1, 1, 3, 5, true, false, true, false, ACT_NONE, 0, 0},
   };
@@ -280,8 +338,13 @@ int main(int argc, char** argv) {
   };
   int fails = 0;
   try {
-    if (!only)
+    if (!only) {
       for (auto& c : cases) fails += run_case(c, false) ? 0 : 1;
+      fails += check_batch_invariance(2, 8, 1280, 1280, true, false) ? 0 : 1;
+      fails += check_batch_invariance(16, 8, 1280, 1280, false, true) ? 0 : 1;
+      fails += check_batch_invariance(3, 4, 1280, 640, true, true) ? 0 : 1;
+      fails += check_batch_invariance(2, 16, 640, 640, false, false) ? 0 : 1;  // not split: the plain schedule
+    }
     if (bench)
       for (auto& c : bench_cases)
         if (!only || strstr(c.name, only)) fails += run_case(c, true) ? 0 : 1;

@@ -187,6 +187,21 @@ def test_batched_cfg_equals_separate_calls(engine_unet):
     assert np.array_equal(both[:B], a) and np.array_equal(both[B:], b)
 
 
+def test_full_size_batching_and_determinism(engine_unet):
+    """BASELINE-size latent (64x64): a UNet call is bit-identical when repeated and when its samples are evaluated in
+    one batch or one by one (the one-kernel GroupNorm's partition and the split-K reduction order depend on the
+    tensor shape only, never on the batch)"""
+    B, h = 2, 64
+    lat, ctx = synth.latents(B, h, h, seed=11), synth.context(B, seed=12)
+    te = temb(300, B)
+    both = engine_unet.unet(lat, te, ctx)
+    again = engine_unet.unet(lat, te, ctx)
+    one = engine_unet.unet(lat[1:], te[1:], ctx[1:])
+    assert np.isfinite(both).all()
+    assert np.array_equal(both, again)
+    assert np.array_equal(both[1:], one)
+
+
 def test_img2img_inpaint_controlnet_tcd_paths(engine_unet, engine_vae, engine_cnet, unet_sd, vae_sd, cnet_sd):
     """configs 3, 4 and 5b at reduced size against the oracle loop (free-running, so the bar is looser than per-call)"""
     B, h, H = 1, 16, 128
