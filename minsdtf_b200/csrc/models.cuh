@@ -699,17 +699,27 @@ inline void text_encode(Ctx& c, const TextW& t, const int* tokens, int B, int T,
   const int n_layers = kClipLayers + clip_skip + 1;
   const size_t m0 = c.ws->mark();
   const long long rows = (long long)B * T;
-  View x = c.alloc_view(1, 1, (int)rows, C), h = c.alloc_view(1, 1, (int)rows, C), a = c.alloc_view(1, 1, (int)rows, C);
+  // residual stream x in fp32; GEMM operands (h, a, f) and GEMM outputs (qkv, d) in bf16
+  float* x = c.ws->alloc_n<float>((size_t)rows * C);
+  View h = c.alloc_view(1, 1, (int)rows, C), a = c.alloc_view(1, 1, (int)rows, C), d = c.alloc_view(1, 1, (int)rows, C);
   View qkv = c.alloc_view(1, 1, (int)rows, 3 * C), f = c.alloc_view(1, 1, (int)rows, 4 * C);
+  SDTF_CHECK(C == 768, "text tower: embed_dim must be 768");
+  auto add_ln = [&](const bf16* delta, const NormW& n, bf16* out_bf16, float* out_f32) {
+    ++c.launches;
+    if (c.dry) return;
+    clip_add_ln_kernel<6><<<(unsigned)ceil_div_ll(rows, 8), 256, 0, c.st>>>(x, delta, C, rows, n.gamma, n.beta, out_bf16, out_f32);
+    SDTF_CUDA(cudaGetLastError());
+  };
   ++c.launches;
   if (!c.dry) {
     long long blocks = ceil_div_ll(rows * (C / 4), 256);
-    clip_embed_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(tokens, t.tok, t.pos, t.vocab, T, C, rows, x.p);
+    clip_embed_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(tokens, t.tok, t.pos, t.vocab, T, C, rows, x);
     SDTF_CUDA(cudaGetLastError());
   }
+  const bf16* pending = nullptr;  // GEMM output not yet added to the stream
   for (int l = 0; l < n_layers; ++l) {
     const TextLayerW& L = t.layer[l];
-    c.layernorm(x, L.ln1, h);
+    add_ln(pending, L.ln1, h.p, nullptr);
     c.conv(h, L.qkv, qkv);
     ++c.launches;
     if (!c.dry) {
@@ -717,13 +727,13 @@ inline void text_encode(Ctx& c, const TextW& t, const int* tokens, int B, int T,
       clip_causal_attn_kernel<<<dim3(kClipHeads, B), 128, smem, c.st>>>(qkv.p, T, C, a.p);
       SDTF_CUDA(cudaGetLastError());
     }
-    c.conv(a, L.out, x, 1, -1, &x);
-    c.layernorm(x, L.ln2, h);
+    c.conv(a, L.out, d);
+    add_ln(d.p, L.ln2, h.p, nullptr);
     c.conv(h, L.fc1, f, 1, -1, nullptr, nullptr, 0, ACT_QGELU);
-    c.conv(f, L.fc2, x, 1, -1, &x);
+    c.conv(f, L.fc2, d);
+    pending = d.p;
   }
-  c.layernorm(x, t.final_ln, h);
-  c.cast_out(h.p, C, rows, C, out);
+  add_ln(pending, t.final_ln, nullptr, out);
   c.ws->release(m0);
 }
 

@@ -7,7 +7,7 @@ from minsdtf_b200 import synth
 from oracle import text_oracle as TO
 
 pytestmark = pytest.mark.gpu
-TEXT_BAR = 2e-2  # max |d| / max |ref| of the (B,77,768) context: bf16 activations vs the fp32 oracle
+TEXT_BAR = 1e-2  # max |d| / max |ref| of the (B,77,768) context: bf16 GEMM operands, fp32 residual stream, vs the fp32 oracle
 
 
 @pytest.fixture(scope="module")
