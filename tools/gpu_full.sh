@@ -1,6 +1,7 @@
 #!/bin/bash
 # One full GPU visit: parity tests, both bench arms, ncu launch list of a 2-step generation, and ncu --set full captures
-# of the dominant kernels (implicit-GEMM conv, d=40 self-attention, GroupNorm apply).  Outputs under gpurun_out/.
+# of the dominant kernels (implicit-GEMM conv, d=40 self-attention, one-kernel GroupNorm, cross-attention) and the
+# SDTF_TRACE operator table.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/gpu_tests.log
 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_engine.json 2> gpurun_out/bench_engine.err
@@ -22,10 +23,11 @@ tail -1 gpurun_out/ncu_full_conv.log
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn2 -s 2 -c 1 -f -o gpurun_out/full_attn_self64 \
   python tools/bench_kernels.py attn > gpurun_out/ncu_full_attn.log 2>&1
 tail -1 gpurun_out/ncu_full_attn.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gn_apply -s 8 -c 1 -f -o gpurun_out/full_gn_apply \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:gn_fused -s 8 -c 1 -f -o gpurun_out/full_gn_fused \
   python bench.py --steps 1 --warmup 0 --denoise-steps 1 --no-graph --skip-cpu-baseline --profile-only > gpurun_out/ncu_full_gn.log 2>&1
 tail -1 gpurun_out/ncu_full_gn.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gn_stats -s 8 -c 1 -f -o gpurun_out/full_gn_stats \
-  python bench.py --steps 1 --warmup 0 --denoise-steps 1 --no-graph --skip-cpu-baseline --profile-only > gpurun_out/ncu_full_gns.log 2>&1
-tail -1 gpurun_out/ncu_full_gns.log
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:xattn -s 1 -c 1 -f -o gpurun_out/full_xattn \
+  python tools/bench_kernels.py attn > gpurun_out/ncu_full_xattn.log 2>&1
+tail -1 gpurun_out/ncu_full_xattn.log
+SDTF_TRACE=1 python bench.py --steps 1 --warmup 1 --denoise-steps 2 --no-graph --skip-cpu-baseline --profile-only > gpurun_out/trace.out 2> gpurun_out/trace.log
 ls -la gpurun_out
