@@ -103,6 +103,14 @@ def measured_peak():
     return FALLBACK_PEAK_TFLOPS, "fallback (B200_PROFILING.md)"
 
 
+def measured_sustained_peak():
+    """cuBLAS bf16 throughput back to back for seconds (power-capped clocks): the right denominator for a whole step"""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle on host cores
 # ----------------------------------------------------------------------------------------------------------------
@@ -310,6 +318,7 @@ def run_engine(args, rank, world, local_rank):
                     "d2h_bytes_per_step": int(B * size * size * 3), "ms_per_step": wall_e2e / K * 1e3},
             "gpu_launches": int(launches),
             "unet_step_ms": unet_step_ms, "unet_step_tflops": unet_tflops, "unet_step_frac_of_peak": unet_tflops / peak,
+            "unet_step_frac_of_sustained_peak": (unet_tflops / measured_sustained_peak()) if measured_sustained_peak() else None,
             "decode_ms_per_batch": dec_ms / K, "wall_ms_per_step": wall / K * 1e3,
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
                          "traffic": ncu_traffic(conv_label), "kernel": conv_label,

@@ -586,7 +586,9 @@ template <int N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 2, 512;" ::: "memory"); }
 
-template <int KS, int DV>
+// DEFER (A/B switch SDTF_ATTN_DEFER = 0 | 16 | 32): exponentials of the first DEFER keys of a tile are computed into
+// registers BEFORE waiting for P V_{j-1} (the wait only guards the P buffer and the rare O rescale).
+template <int KS, int DV, int DEFER>
 __global__ void __launch_bounds__(kAHThreads, 1)
 attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -768,11 +770,19 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mx = fmax3(mx, mx2, fmaxf(__uint_as_float(sv[62]), __uint_as_float(sv[63])));
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const bool grow = (m_new - m_run) > 8.f;  // (-inf) - (-inf) = NaN -> false: nothing to move
-      if (j > 0) {  // P V_{j-1} of this half must be complete before O is touched or P overwritten
+      // P V_{j-1} of this half must be complete before O is touched or P overwritten
+      bool waited = (j == 0);
+      if (DEFER == 0 && !waited) {
         mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
         fence_after_sync();
+        waited = true;
       }
       if (__any_sync(0xffffffffu, grow)) {
+        if (!waited) {
+          mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+          fence_after_sync();
+          waited = true;
+        }
         const float alpha = grow ? ex2f(m_run - m_new) : 1.f;
         if (grow) m_run = m_new;
         if (j > 0) {
@@ -789,20 +799,30 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
       }
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;  // no valid key yet: every term below becomes 2^-inf = 0
-#pragma unroll
-      for (int c = 0; c < 64; c += 8) {
+      // (masked keys were set to -inf above: 2^-inf = 0 on the MUFU path, 2^-126 on the FMA path — below anything bf16 keeps)
+      auto exp8 = [&](int c) {
         float e[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float xarg = fmaf(__uint_as_float(sv[c + i]), p.scale_log2, neg_m);
           e[i] = (i >= 6) ? ex2_poly(xarg) : ex2f(xarg);  // 2 of 8 on the FMA pipe
         }
-        // (masked keys were set to -inf above: 2^-inf = 0 on the MUFU path, 2^-126 on the FMA path — below anything bf16 keeps)
         uint4 w;
         w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]);
         w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
-        *reinterpret_cast<uint4*>(rowp + (((c >> 3) ^ sw) << 4)) = w;
+        return w;
+      };
+      uint4 early[DEFER / 8 + 1];
+#pragma unroll
+      for (int c = 0; c < DEFER; c += 8) early[c >> 3] = exp8(c);
+      if (!waited) {
+        mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+        fence_after_sync();
       }
+#pragma unroll
+      for (int c = 0; c < DEFER; c += 8) *reinterpret_cast<uint4*>(rowp + (((c >> 3) ^ sw) << 4)) = early[c >> 3];
+#pragma unroll
+      for (int c = DEFER; c < 64; c += 8) *reinterpret_cast<uint4*>(rowp + (((c >> 3) ^ sw) << 4)) = exp8(c);
       fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
       fence_before_sync();
       __syncwarp();
@@ -1151,7 +1171,9 @@ inline void init_attn_kernels() {
   static_assert(attn2q_smem_bytes<2, 2, 1>() <= 232448, "d = 80 two-tile attention must fit 227 KB of shared memory");
   SDTF_CUDA(cudaFuncSetAttribute(attn2q_kernel<2, 5, 80, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)attn2q_smem_bytes<2, 2, 1>()));
-  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
   init_attn_t<2, 5, 80, 2, 2>();
   init_attn_t<3, 10, 160, 1, 1>();
   static_assert(xattn_smem_bytes<2, 3>() <= 232448, "d = 80 cross-attention must fit 227 KB of shared memory");
@@ -1214,7 +1236,10 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
       static const int use_2q = getenv("SDTF_ATTN_2Q") ? atoi(getenv("SDTF_ATTN_2Q")) : 0;  // A/B: previous full-row kernel
       if (!use_2q) {
         SDTF_CHECK(a.d < 48, "attn2h keeps the softmax denominator in accumulator column d: needs d < DV");
-        launch_pdl(attn2h_kernel<3, 48>, grid, dim3(kAHThreads), attn2h_smem_bytes(), stream, 1, tq, tk, tv, p);
+        static const int defer = getenv("SDTF_ATTN_DEFER") ? atoi(getenv("SDTF_ATTN_DEFER")) : 16;  // measured: 0.735 / 0.724 / 0.756 ms for 0 / 16 / 32
+        if (defer == 16) launch_pdl(attn2h_kernel<3, 48, 16>, grid, dim3(kAHThreads), attn2h_smem_bytes(), stream, 1, tq, tk, tv, p);
+        else if (defer == 32) launch_pdl(attn2h_kernel<3, 48, 32>, grid, dim3(kAHThreads), attn2h_smem_bytes(), stream, 1, tq, tk, tv, p);
+        else launch_pdl(attn2h_kernel<3, 48, 0>, grid, dim3(kAHThreads), attn2h_smem_bytes(), stream, 1, tq, tk, tv, p);
         SDTF_CUDA(cudaGetLastError());
         return;
       }
