@@ -50,7 +50,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // The previous two-kernel version (statistics, then apply) paid two launches, a serial last-CTA reduction and a
 // second cold ramp per GroupNorm: 3.2 ms of a 18.8 ms denoise step for 61 GroupNorms.
 // ------------------------------------------------------------------------------------------------------
-static constexpr int kGnMaxBlk = 64;
+static constexpr int kGnMaxBlk = 128;
 
 struct GnScratch {
   double* partial = nullptr;    // [B][kGnMaxBlk][64]
@@ -250,10 +250,19 @@ inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, 
   SDTF_CHECK(smem <= kGnMaxSmem, "GroupNorm: reduction scratch exceeds the shared-memory budget the occupancy was computed for");
   // CTAs per sample: a function of (HW, C) only, so statistics do not depend on how samples are batched.
   // ~32 KB of the sample per CTA (four 16-byte vectors per thread: one round of loads per phase) up to 16 CTAs — a UNet
-  // batch of 16 is then one co-resident round on 148 SMs — and up to 32 for the VAE's 16+ MB samples.
+  // batch of 16 is then one co-resident round on 148 SMs.  The VAE's 16+ MB samples get 1 MB per CTA, 32 to 64 CTAs
+  // (measured: 128 CTAs per sample makes a single image's decode 1.3 ms faster but a batch of 8, walked in four rounds,
+  // 0.8 ms slower; 64 keeps the batch at two rounds).
   const long long bytes = HW * x.C * 2;
   long long nblk = ceil_div_ll(bytes, 32 * 1024);
-  if (nblk > 16) nblk = bytes > (16LL << 20) ? 32 : 16;
+  if (nblk > 16) {
+    nblk = 16;
+    if (bytes > (16LL << 20)) {
+      nblk = ceil_div_ll(bytes, 1024 * 1024);
+      if (nblk < 32) nblk = 32;
+      if (nblk > 64) nblk = 64;
+    }
+  }
   if (nblk > HW / lanes) nblk = HW / lanes;
   if (nblk < 1) nblk = 1;
   const long long ppc = ceil_div_ll(HW, nblk);
