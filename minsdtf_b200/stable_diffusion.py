@@ -100,7 +100,9 @@ class StableDiffusionBase:
                 raise NotImplementedError(
                     "no tokenizer: the CLIP BPE vocabulary cannot be downloaded offline — set `model.tokenizer` (an object with "
                     ".encode(str) -> token ids), or pass token ids / an encoded (T,768) array as `prompt`")
-            ids = list(tok.encode(prompt))[:MAX_PROMPT_LENGTH]
+            ids = list(tok.encode(prompt))
+            if len(ids) > MAX_PROMPT_LENGTH:  # as the reference's tokenizer path: truncate, keep the end token
+                ids = ids[:MAX_PROMPT_LENGTH - 1] + [49407]
             ids = ids + [49407] * (MAX_PROMPT_LENGTH - len(ids))
             prompt = np.asarray(ids, np.int32)
         tokens = np.asarray(prompt)
@@ -190,6 +192,17 @@ class StableDiffusionBase:
             else:
                 uncond = self._expand_tensor(self.encode_text("" if negative_prompt is None else negative_prompt,
                                                               negative_embedding), batch_size)
+            # long prompts: both contexts must span the same number of 77-token windows; the shorter one is continued
+            # with empty-prompt windows, as the reference pads it (long_prompt_weighting.py)
+            tc, tu = context.shape[1], uncond.shape[1]
+            if tc != tu:
+                if tc % MAX_PROMPT_LENGTH or tu % MAX_PROMPT_LENGTH:
+                    raise ValueError(f"context lengths {tc} and {tu} differ and are not multiples of 77")
+                empty = np.repeat(self._get_unconditional_context(), batch_size, axis=0)
+                if tu < tc:
+                    uncond = np.concatenate([uncond] + [empty] * ((tc - tu) // MAX_PROMPT_LENGTH), axis=1)
+                else:
+                    context = np.concatenate([context] + [empty] * ((tu - tc) // MAX_PROMPT_LENGTH), axis=1)
         if diffusion_noise is not None:
             diffusion_noise = np.squeeze(diffusion_noise)
             if diffusion_noise.ndim == 3:
@@ -380,10 +393,22 @@ class StableDiffusion(StableDiffusionBase):
         return _Model(lambda tokens: self.engine.text_encode(tokens, self.clip_skip))
 
     def _encode_tokens(self, tokens):
+        """(T,) / (B,T) token ids -> (T,768) / (B,T,768).  T > 77 must be a multiple of 77: each 77-token window is
+        encoded on its own and the contexts are concatenated, which is how the reference feeds long prompts to the
+        UNet (long_prompt_weighting.py: chunks of <start> + 75 tokens + <end>), giving contexts of 154, 231, ... tokens."""
         self._ensure("text_encoder", self.text_encoder_ckpt)
         tokens = np.asarray(tokens, np.int32)
-        out = self.engine.text_encode(tokens, self.clip_skip)
-        return out[0] if tokens.ndim == 1 else out
+        one = tokens.ndim == 1
+        tok2 = tokens[None] if one else tokens
+        B, T = tok2.shape
+        if T > MAX_PROMPT_LENGTH:
+            if T % MAX_PROMPT_LENGTH:
+                raise ValueError(f"token ids: length {T} is neither <= 77 nor a multiple of 77")
+            m = T // MAX_PROMPT_LENGTH
+            out = self.engine.text_encode(tok2.reshape(B * m, MAX_PROMPT_LENGTH), self.clip_skip).reshape(B, T, -1)
+        else:
+            out = self.engine.text_encode(tok2, self.clip_skip)
+        return out[0] if one else out
 
     def generate_image(self, encoded_text, **kw):
         self._ensure("unet", self.unet_ckpt)

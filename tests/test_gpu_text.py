@@ -67,3 +67,26 @@ def test_token_ids_to_image_through_public_api(engine_text, engine_unet, engine_
     # the reference's two-model composition (stable_diffusion.py:700-725) gives the same context
     two = sd.text_encoder.predict_on_batch(sd.text_clip_embedding.predict_on_batch([tokens[None], sd._get_pos_ids()]))
     assert np.array_equal(two[0], ctx)
+
+
+def test_long_prompt_windows_and_string_prompts(engine_text, engine_unet, engine_vae, tmp_path):
+    """154 token ids = two 77-token windows encoded separately and concatenated; a string goes through model.tokenizer"""
+    import gzip
+    from minsdtf_b200.bpe import ClipBPE
+    from minsdtf_b200.stable_diffusion import StableDiffusion
+    sd = StableDiffusion(img_height=128, img_width=128, synthetic=True, engine=engine_text)
+    tok = synth.prompt_tokens(2)
+    long_ids = np.concatenate([tok[0], tok[1]])
+    ctx = sd.encode_text(long_ids)
+    assert ctx.shape == (154, 768)
+    assert np.array_equal(ctx[:77], sd.encode_text(tok[0])) and np.array_equal(ctx[77:], sd.encode_text(tok[1]))
+    # guidance on: the 77-token unconditional context is continued with an empty-prompt window to 154 tokens
+    img = sd.generate_image(ctx, batch_size=1, num_steps=2, diffusion_noise=synth.latents(1, 16, 16), unconditional_guidance_scale=7.5)
+    assert img.shape == (1, 128, 128, 3) and img.dtype == np.uint8
+    gz = tmp_path / "v.txt.gz"
+    with gzip.open(gz, "wb") as f:
+        f.write(b"#version\nh e\nl l\nhe ll\nhell o</w>\n")
+    sd.tokenizer = ClipBPE(str(gz))
+    c = sd.encode_text("hello hello")
+    ids = sd.tokenizer.encode("hello hello")
+    assert c.shape == (77, 768) and len(ids) == 4
