@@ -39,3 +39,13 @@ def test_oracle_matches_transformers_clip(clip_skip):
 def test_unconditional_tokens_shape():
     tok = synth.prompt_tokens(3)
     assert tok.shape == (3, 77) and tok.dtype == np.int32 and (tok[:, 0] == 49406).all() and (tok[:, -1] == 49407).all()
+
+
+def test_oracle_matches_committed_transformers_golden():
+    """the same check against the committed fixture (no transformers import needed where the tests run)"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "text_tower.npz"))
+    sd = synth.make_state_dict("text_encoder")
+    for skip, key in ((-1, "ctx_skip1"), (-2, "ctx_skip2")):
+        got = T.text_encode(sd, g["tokens"], skip)[..., ::4]
+        assert np.abs(got - g[key].astype(np.float32)).max() <= 2e-3 * float(g["max_abs"])  # float16 storage of the fixture

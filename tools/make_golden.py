@@ -140,7 +140,33 @@ def table_golden():
     print("alias mismatches:", bad[:5], len(bad))
 
 
+def text_tower_golden():
+    """tests/golden/text_tower.npz: outputs of transformers.CLIPTextModel (an implementation of the text tower that is
+    independent of this repository and of its oracle) on the seeded synthetic text-encoder weights: tokens (2,77) and the
+    context for clip_skip -1 / -2, every 4th channel, float16.  The Keras TextEncoder of the reference cannot be run
+    here; its checkpoint (`text_encoder/model.safetensors`, text_encoder.py:112) is the HF CLIPTextModel's."""
+    import torch
+    import transformers
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from minsdtf_b200 import synth
+    sd = synth.make_state_dict("text_encoder")
+    cfg = transformers.CLIPTextConfig(vocab_size=49408, hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                                      num_attention_heads=12, max_position_embeddings=77, hidden_act="quick_gelu",
+                                      layer_norm_eps=1e-5, eos_token_id=49407, bos_token_id=49406, pad_token_id=49407)
+    model = transformers.CLIPTextModel(cfg).eval()
+    model.load_state_dict(sd, strict=False)
+    tokens = synth.prompt_tokens(2)
+    with torch.no_grad():
+        out = model(input_ids=torch.as_tensor(tokens, dtype=torch.long), output_hidden_states=True)
+        c1 = out.last_hidden_state.numpy()
+        c2 = model.text_model.final_layer_norm(out.hidden_states[-2]).numpy()
+    np.savez_compressed(os.path.join(OUT, "text_tower.npz"), tokens=tokens, ctx_skip1=c1[..., ::4].astype(np.float16),
+                        ctx_skip2=c2[..., ::4].astype(np.float16), max_abs=np.float32(np.abs(c1).max()))
+    print("text tower golden:", c1.shape, float(np.abs(c1).max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     scheduler_golden()
     table_golden()
+    text_tower_golden()
