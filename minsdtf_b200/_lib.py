@@ -50,12 +50,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SDTF_LIB") or LIB_PATH  # SDTF_LIB: an alternative build of the same library (A/B measurements)
+    if path == LIB_PATH and not os.path.exists(LIB_PATH):
         from . import build
         build.build_lib()
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m minsdtf_b200.build` — there is no fallback path")
-    lib = ctypes.CDLL(LIB_PATH)
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m minsdtf_b200.build` — there is no fallback path")
+    lib = ctypes.CDLL(path)
     vp, i32 = ctypes.c_void_p, ctypes.c_int32
     lib.sdtf_create.argtypes = [i32, ctypes.POINTER(vp)]
     lib.sdtf_destroy.argtypes = [vp]
