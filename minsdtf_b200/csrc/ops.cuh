@@ -691,12 +691,17 @@ cfg_sched_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_
   const bool cfg = c.guidance > 0.f && eps_u != nullptr;
   float factor = 1.f;
   if (cfg && c.rescale > 0.f) {
-    // population std of eps_c and of the combined eps over the whole sample (two-pass, fp32)
+    // population std of eps_c and of the combined eps over the whole sample (two-pass, fp32); 16-byte loads (n_per_sample
+    // is a multiple of 4: h*w*4 channels) — the sample's 128 KB stay in L1 for the second and third pass
+    const int n4 = n_per_sample >> 2;
+    const float4* u4 = reinterpret_cast<const float4*>(eps_u + off);
+    const float4* t4 = reinterpret_cast<const float4*>(eps_c + off);
     float s1 = 0.f, s2 = 0.f;
-    for (int i = threadIdx.x; i < n_per_sample; i += blockDim.x) {
-      const float u = eps_u[off + i], t = eps_c[off + i];
-      s1 += t;
-      s2 += u + c.guidance * (t - u);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 u = u4[i], t = t4[i];
+      s1 += (t.x + t.y) + (t.z + t.w);
+      s2 += ((u.x + c.guidance * (t.x - u.x)) + (u.y + c.guidance * (t.y - u.y))) +
+            ((u.z + c.guidance * (t.z - u.z)) + (u.w + c.guidance * (t.w - u.w)));
     }
     s1 = warp_sum(s1); s2 = warp_sum(s2);
     if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s1; red[1][threadIdx.x >> 5] = s2; }
@@ -709,11 +714,15 @@ cfg_sched_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_
     __syncthreads();
     const float m1 = stat[0], m2 = stat[1];
     float q1 = 0.f, q2 = 0.f;
-    for (int i = threadIdx.x; i < n_per_sample; i += blockDim.x) {
-      const float u = eps_u[off + i], t = eps_c[off + i];
-      const float e = u + c.guidance * (t - u);
-      q1 += (t - m1) * (t - m1);
-      q2 += (e - m2) * (e - m2);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 u = u4[i], t = t4[i];
+      const float uu[4] = {u.x, u.y, u.z, u.w}, tt[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float e = uu[k] + c.guidance * (tt[k] - uu[k]);
+        q1 += (tt[k] - m1) * (tt[k] - m1);
+        q2 += (e - m2) * (e - m2);
+      }
     }
     q1 = warp_sum(q1); q2 = warp_sum(q2);
     __syncthreads();
