@@ -57,6 +57,8 @@ struct GnScratch {
   unsigned* counters = nullptr; // [B], zero between launches (self-resetting)
   unsigned* gens = nullptr;     // [B], barrier generation (monotonic)
   float* stats = nullptr;       // [B][64]: mean, rstd per group (kept for debugging / tests)
+  int share = 1;                // launches of this scratch may run next to (share - 1) other GroupNorm kernels: each gets
+                                // 1/share of the co-resident CTA slots (two spinning kernels must fit the device TOGETHER)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -267,7 +269,7 @@ inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, 
   if (nblk < 1) nblk = 1;
   const long long ppc = ceil_div_ll(HW, nblk);
   nblk = ceil_div_ll(HW, ppc);
-  long long by = g_gn_resident_ctas / nblk;  // samples per round: every CTA of the grid must be resident
+  long long by = (g_gn_resident_ctas / (sc.share > 0 ? sc.share : 1)) / nblk;  // samples per round: every CTA of the grid must be resident
   if (by > x.B) by = x.B;
   SDTF_CHECK(by >= 1, "GroupNorm: a sample's CTAs do not fit on the device at once");
   dim3 grid((unsigned)nblk, (unsigned)by);
