@@ -908,9 +908,9 @@ constexpr size_t attn_smem_bytes() {
 // head): K and V land in shared memory once, and the head's query tiles stream through a warp-specialised pipeline:
 //   warp 9      TMA: K, V, then a QST-deep ring of Q tiles
 //   warp 8      MMA: S_t = Q_t K^T into TMEM buffer t&1, then O_{t-1} = P_{t-1} V into accumulator (t-1)&1
-//   warps 0-3   softmax of tile t: a thread owns a row; one pass (all keys are in the tile: no running max, no
-//               rescale), row sum kept in registers and handed to the epilogue through shared memory
-//   warps 4-7   epilogue of tile t: O / l -> bf16 -> global, while the softmax warps are already on tile t+1
+//   warps 0-7   two groups of four; group g owns tiles t = g, g+2, ... and S / P / O buffer g: softmax of tile t (a
+//               thread owns a row; one pass — all keys are in the tile: no running max, no rescale), then, once P V_t
+//               has landed, O / l -> bf16 -> global; the other group's exponentials run meanwhile
 // ------------------------------------------------------------------------------------------------------
 static constexpr int kXAThreads = 320;
 
@@ -946,7 +946,6 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
   const uint32_t tmem_slot = bb + 80u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
-  float* lbuf = reinterpret_cast<float*>(gen + (sL - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x, b = blockIdx.y;
@@ -1028,13 +1027,18 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
     }
     __syncwarp();
-  } else if (warp < 4) {
-    // ===== softmax: thread = query row =====
-    const int row = warp * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+  } else {
+    // ===== softmax + epilogue: two groups of four warps; group g owns the tiles t = g, g + 2, ... and with them S / P / O
+    // buffer g.  A thread is a query row: softmax of tile t, then (once P V_t has landed) O / l -> bf16 -> global.  While one
+    // group waits for its P V or stores its rows, the other group's exponentials keep the MUFU busy (one group alone ran
+    // a tile in 2700 cycles against a MUFU floor of 640).
+    const int g = warp >> 2, q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
     const int sw = row & 7;
-    for (int t = 0; t < nqt; ++t) {
-      const int sb = t & 1, u = t >> 1;
+    const int sb = g;  // buffer index == group
+    uint8_t* rowp = gen + (sP - base) + (uint32_t)(2 * sb) * kChunk + row * 128;
+    for (int t = g, u = 0; t < nqt; t += 2, ++u) {
       mbar_wait(s_full(sb), (uint32_t)u & 1u);
       fence_after_sync();
       constexpr int NL = (NC + 31) / 32 * 32;  // columns loaded (whole 32-column TMEM loads)
@@ -1051,7 +1055,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 #pragma unroll
       for (int i = 0; i < NC; ++i)
         if (i >= p.Nk) sv[i] = 0xff800000u;
-      float mxa = -INFINITY, mxb = -INFINITY;  // two independent chains (one warp per scheduler: latency is not hidden)
+      float mxa = -INFINITY, mxb = -INFINITY;  // two independent chains
 #pragma unroll
       for (int c = 0; c < NC; c += 8) {
         mxa = fmax3(mxa, __uint_as_float(sv[c]), __uint_as_float(sv[c + 1]));
@@ -1061,58 +1065,38 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
       const float scale = p.scale_log2;
       const float neg_m = -fmaxf(mxa, mxb) * scale;
-      uint32_t pk[NC / 2];
       float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+      // (the P buffer and accumulator of this group are free: its previous tile's epilogue finished in program order)
 #pragma unroll
       for (int c = 0; c < NC; c += 8) {
         float e[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) e[i] = ex2f(fmaf(__uint_as_float(sv[c + i]), scale, neg_m));
         ls0 += e[0] + e[1]; ls1 += e[2] + e[3]; ls2 += e[4] + e[5]; ls3 += e[6] + e[7];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pk[(c >> 1) + i] = pack_bf16(e[2 * i], e[2 * i + 1]);
-      }
-      if (u >= 1) {  // P V of tile t-2 has been read out by the epilogue: P buffer, row sums and accumulator sb are free
-        mbar_wait(o_free(sb), (uint32_t)(u - 1) & 1u);
-        fence_after_sync();
-      }
-      uint8_t* rowp = gen + (sP - base) + (uint32_t)(2 * sb) * kChunk + row * 128;
-#pragma unroll
-      for (int c = 0; c < NC; c += 8) {
+        uint4 w;
+        w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]);
+        w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
         const int chunk = c >> 6, un = (c & 63) >> 3;
-        *reinterpret_cast<uint4*>(rowp + chunk * kChunk + ((un ^ sw) << 4)) =
-            make_uint4(pk[(c >> 1)], pk[(c >> 1) + 1], pk[(c >> 1) + 2], pk[(c >> 1) + 3]);
+        *reinterpret_cast<uint4*>(rowp + chunk * kChunk + ((un ^ sw) << 4)) = w;
       }
-      const float lsum = (ls0 + ls1) + (ls2 + ls3);
-      lbuf[sb * 128 + row] = lsum;
+      const float inv_l = 1.f / ((ls0 + ls1) + (ls2 + ls3));
       fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full(sb));
-    }
-  } else {
-    // ===== epilogue: O / l -> bf16 =====
-    const int q4 = warp - 4;
-    const int row = q4 * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(q4 * 32) << 16;
-    for (int t = 0; t < nqt; ++t) {
-      const int ob = t & 1, u = t >> 1;
-      mbar_wait(p_full(ob), (uint32_t)u & 1u);  // release/acquire with the softmax threads: the row sums are visible
-      mbar_wait(o_full(ob), (uint32_t)u & 1u);
+      // ---- epilogue of the same tile ----
+      mbar_wait(o_full(sb), (uint32_t)u & 1u);
       fence_after_sync();
       uint32_t o[DV];
 #pragma unroll
       for (int c = 0; c < DV; c += 16) {
         uint32_t v[16];
-        tmem_ld16(tmem + 256u + kOStride * ob + lane_off + c, v);
+        tmem_ld16(tmem + 256u + kOStride * sb + lane_off + c, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[c + i] = v[i];
       }
       tmem_ld_wait();
-      const float inv_l = 1.f / lbuf[ob * 128 + row];
       fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free(ob));
       const int q = t * 128 + row;
       if (q < p.Nq) {
         bf16* orow = p.out + ((long long)b * p.Nq + q) * p.ldo + head * p.d;
