@@ -81,7 +81,9 @@ typedef struct {
                                               are exchanged with one ncclAllGather per step */
   const DLManagedTensor* latent0;          /* (B,h,w,4) f32 start latent (noise, or noised init for img2img) */
   const DLManagedTensor* context;          /* (B,T,768) f32 */
-  const DLManagedTensor* uncond_context;   /* (B,T,768) f32, NULL when guidance == 0 */
+  const DLManagedTensor* uncond_context;   /* (B,Tu,768) f32, NULL when guidance == 0.  Tu may differ from T (a long
+                                              prompt against a short negative prompt): the two branches are then
+                                              evaluated as two passes, like the reference's two model calls */
   const DLManagedTensor* t_emb;            /* (n_steps,320) f32 sinusoidal embeddings in execution order */
   const sdtf_step_coef* coefs;             /* [n_steps] host array, execution order */
   const DLManagedTensor* step_noise;       /* (n_steps,B,h,w,4) f32 TCD noise, or NULL */
@@ -93,6 +95,10 @@ typedef struct {
   const DLManagedTensor* blend_mask;       /* (H,W) f32 */
   DLManagedTensor* out_images;             /* (B,H,W,3) u8 (decode=1) */
   DLManagedTensor* out_latent;             /* (B,h,w,4) f32 final latent, or NULL */
+  /* `callback(iteration)` of generate_image (stable_diffusion.py:476-478), or NULL: called on the calling thread
+   * after every denoising step has completed on the device, iteration = 1..n_steps */
+  void (*on_step)(int32_t iteration, void* user);
+  void* on_step_user;
 } sdtf_denoise_desc;
 
 typedef struct {
@@ -138,6 +144,16 @@ int sdtf_vae_encode(sdtf_engine* e, const DLManagedTensor* image, DLManagedTenso
  * tokens (B,T<=77) int32 -> context (B,T,768) f32; clip_skip in [-12,-1] selects the encoder layer whose output is
  * normalised (text_encoder.py:133).  Component "text_encoder", keys text_model.* (text_encoder.py:110-111,137-157). */
 int sdtf_text_encode(sdtf_engine* e, const DLManagedTensor* tokens, int clip_skip, DLManagedTensor* out_context);
+
+/* The reference's two text models separately, for textual inversion, which splices learned vectors between them
+ * (long_prompt_weighting.py:202-209, 231-235):
+ *   sdtf_text_embed            TextClipEmbedding.predict_on_batch([tokens, positions]) — text_encoder.py:22-33,106-122:
+ *                              tokens (B,T) int32, positions (1,T) or (B,T) int32 or NULL (0..T-1) -> (B,T,768) f32
+ *   sdtf_text_encode_embedded  TextEncoder.predict_on_batch(clip_embedding) — text_encoder.py:125-135:
+ *                              embedding (B,T,768) f32 -> context (B,T,768) f32 */
+int sdtf_text_embed(sdtf_engine* e, const DLManagedTensor* tokens, const DLManagedTensor* positions,
+                    DLManagedTensor* out_embedding);
+int sdtf_text_encode_embedded(sdtf_engine* e, const DLManagedTensor* embedding, int clip_skip, DLManagedTensor* out_context);
 
 /* CFG combine + rescale + Scheduler.step (+ inpaint blend) as ONE kernel — stable_diffusion.py:458-475,
  * scheduler.py:246-315.  eps_u may be NULL (no guidance).  All (B,h,w,4) f32 except mask (h,w), init_latent (h,w,4). */

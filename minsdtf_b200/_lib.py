@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libsdtf.so")
 EXPORTS = [
     "sdtf_create", "sdtf_destroy", "sdtf_last_error", "sdtf_version", "sdtf_load_tensor", "sdtf_finalize_weights",
     "sdtf_unet_forward", "sdtf_controlnet_forward", "sdtf_hintnet_forward", "sdtf_vae_decode", "sdtf_vae_encode", "sdtf_text_encode",
+    "sdtf_text_embed", "sdtf_text_encode_embedded",
     "sdtf_cfg_sched_step", "sdtf_to_uint8", "sdtf_denoise", "sdtf_get_timings", "sdtf_bench_conv", "sdtf_bench_attention",
     "sdtf_test_attention", "sdtf_test_norm", "sdtf_comm_unique_id", "sdtf_comm_init", "sdtf_comm_destroy",
 ]
@@ -34,7 +35,11 @@ class DenoiseDesc(ctypes.Structure):
                 ("t_emb", ctypes.c_void_p), ("coefs", ctypes.POINTER(StepCoef)), ("step_noise", ctypes.c_void_p),
                 ("mask", ctypes.c_void_p), ("init_latent", ctypes.c_void_p), ("init_noise", ctypes.c_void_p),
                 ("hint_image", ctypes.c_void_p), ("blend_image", ctypes.c_void_p), ("blend_mask", ctypes.c_void_p),
-                ("out_images", ctypes.c_void_p), ("out_latent", ctypes.c_void_p)]
+                ("out_images", ctypes.c_void_p), ("out_latent", ctypes.c_void_p),
+                ("on_step", ctypes.c_void_p), ("on_step_user", ctypes.c_void_p)]
+
+
+ON_STEP = ctypes.CFUNCTYPE(None, ctypes.c_int32, ctypes.c_void_p)  # void (*on_step)(int32_t iteration, void* user)
 
 
 class Timings(ctypes.Structure):
@@ -72,6 +77,8 @@ def load():
     lib.sdtf_vae_decode.argtypes = [vp, vp, vp]
     lib.sdtf_vae_encode.argtypes = [vp, vp, vp]
     lib.sdtf_text_encode.argtypes = [vp, vp, i32, vp]
+    lib.sdtf_text_embed.argtypes = [vp, vp, vp, vp]
+    lib.sdtf_text_encode_embedded.argtypes = [vp, vp, i32, vp]
     lib.sdtf_cfg_sched_step.argtypes = [vp, vp, vp, vp, ctypes.POINTER(StepCoef), vp, vp, vp, vp, vp]
     lib.sdtf_to_uint8.argtypes = [vp, vp, vp, vp, vp]
     lib.sdtf_denoise.argtypes = [vp, ctypes.POINTER(DenoiseDesc)]

@@ -79,6 +79,15 @@ class ClipBPE:
         self._memo[word] = parts
         return parts
 
+    # names the reference's SimpleTokenizer exposes (clip_tokenizer.py:120-126), used by the prompt-weighting code
+    @property
+    def start_of_text(self) -> int:
+        return self.start_id
+
+    @property
+    def end_of_text(self) -> int:
+        return self.end_id
+
     @staticmethod
     def clean(text: str) -> str:
         """html-unescape twice, collapse whitespace, lower-case (clip_tokenizer.py:66-75, 178-180; the optional ftfy

@@ -266,7 +266,20 @@ struct Ctx {
 // ----------------------------------------------------------------------------------------------------------
 struct WeightStore {
   std::unordered_map<std::string, RawTensor> raw;
-  DevicePool pool;
+  // packed weights live in one pool per component, so that re-finalising a component (another checkpoint, LoRA-merged
+  // weights) frees what the previous build of that component allocated
+  std::map<std::string, std::unique_ptr<DevicePool>> pools;
+  struct PoolRef {
+    DevicePool* p = nullptr;
+    void* alloc(size_t n) {
+      SDTF_CHECK(p != nullptr, "WeightStore::begin_component() was not called");
+      return p->alloc(n);
+    }
+  } pool;
+  void begin_component(const std::string& name) {
+    pools[name].reset(new DevicePool());
+    pool.p = pools[name].get();
+  }
   cudaStream_t st = nullptr;
   std::vector<std::string> missing;
 

@@ -692,15 +692,24 @@ inline void build_text_encoder(WeightStore& ws, TextW& t) {
   t.final_ln = ws.norm("text_model.final_layer_norm");
 }
 
-// tokens: [B][T] int32 on the device; out: [B][T][768] fp32.  clip_skip = -1: all 12 layers, -2: 11, ... (reference
-// indexing out[clip_skip], text_encoder.py:133)
-inline void text_encode(Ctx& c, const TextW& t, const int* tokens, int B, int T, int clip_skip, float* out) {
+// TextClipEmbedding (text_encoder.py:22-33): x[b][t] = token_embedding[tokens[b][t]] + position_embedding[pos], fp32
+inline void text_embed(Ctx& c, const TextW& t, const int* tokens, const int* positions, int pos_rows, int B, int T, float* x) {
+  const long long rows = (long long)B * T;
+  ++c.launches;
+  if (c.dry) return;
+  long long blocks = ceil_div_ll(rows * (kCtxDim / 4), 256);
+  clip_embed_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(tokens, positions, pos_rows, t.tok, t.pos, t.vocab, t.max_len, T, kCtxDim, rows, x);
+  SDTF_CUDA(cudaGetLastError());
+}
+
+// TextEncoder (text_encoder.py:125-135) on x: [B][T][768] fp32 embeddings in the arena (overwritten: it is the residual
+// stream); out: [B][T][768] fp32.  clip_skip = -1: all 12 layers, -2: 11, ... (reference indexing out[clip_skip], :133)
+inline void text_encode(Ctx& c, const TextW& t, float* x, int B, int T, int clip_skip, float* out) {
   const int C = kCtxDim;
   const int n_layers = kClipLayers + clip_skip + 1;
   const size_t m0 = c.ws->mark();
   const long long rows = (long long)B * T;
   // residual stream x in fp32; GEMM operands (h, a, f) and GEMM outputs (qkv, d) in bf16
-  float* x = c.ws->alloc_n<float>((size_t)rows * C);
   View h = c.alloc_view(1, 1, (int)rows, C), a = c.alloc_view(1, 1, (int)rows, C), d = c.alloc_view(1, 1, (int)rows, C);
   View qkv = c.alloc_view(1, 1, (int)rows, 3 * C), f = c.alloc_view(1, 1, (int)rows, 4 * C);
   SDTF_CHECK(C == 768, "text tower: embed_dim must be 768");
@@ -710,12 +719,6 @@ inline void text_encode(Ctx& c, const TextW& t, const int* tokens, int B, int T,
     clip_add_ln_kernel<6><<<(unsigned)ceil_div_ll(rows, 8), 256, 0, c.st>>>(x, delta, C, rows, n.gamma, n.beta, out_bf16, out_f32);
     SDTF_CUDA(cudaGetLastError());
   };
-  ++c.launches;
-  if (!c.dry) {
-    long long blocks = ceil_div_ll(rows * (C / 4), 256);
-    clip_embed_kernel<<<(unsigned)blocks, 256, 0, c.st>>>(tokens, t.tok, t.pos, t.vocab, T, C, rows, x);
-    SDTF_CUDA(cudaGetLastError());
-  }
   const bf16* pending = nullptr;  // GEMM output not yet added to the stream
   for (int l = 0; l < n_layers; ++l) {
     const TextLayerW& L = t.layer[l];

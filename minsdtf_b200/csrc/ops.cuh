@@ -534,8 +534,9 @@ inline void launch_skinny_linear(cudaStream_t st, const float* x, int M, int K, 
 // tokens: latency-bound, plain CUDA.
 // ------------------------------------------------------------------------------------------------------
 // x[b][t][:] = token_embedding[tokens[b][t]] + position_embedding[t]  -> fp32 residual stream
-__global__ void clip_embed_kernel(const int* __restrict__ tokens, const float* __restrict__ tok_emb, const float* __restrict__ pos_emb,
-                                  int vocab, int T, int C, long long rows, float* __restrict__ out) {
+__global__ void clip_embed_kernel(const int* __restrict__ tokens, const int* __restrict__ positions /* null: 0..T-1 */, int pos_rows,
+                                  const float* __restrict__ tok_emb, const float* __restrict__ pos_emb, int vocab, int max_len, int T,
+                                  int C, long long rows, float* __restrict__ out) {
   const long long total = rows * (C >> 2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / (C >> 2);
@@ -543,7 +544,10 @@ __global__ void clip_embed_kernel(const int* __restrict__ tokens, const float* _
     int tok = tokens[r];
     tok = tok < 0 ? 0 : (tok >= vocab ? vocab - 1 : tok);
     const float4 a = __ldg(reinterpret_cast<const float4*>(tok_emb + (long long)tok * C + c));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(pos_emb + (long long)(r % T) * C + c));
+    int pos = (int)(r % T);
+    if (positions) pos = positions[pos_rows == 1 ? pos : r];  // (1,T) broadcast over the batch, or (B,T)
+    pos = pos < 0 ? 0 : (pos >= max_len ? max_len - 1 : pos);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(pos_emb + (long long)pos * C + c));
     *reinterpret_cast<float4*>(out + r * C + c) = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
   }
 }
@@ -678,11 +682,11 @@ struct StepCoef {
 };
 
 __global__ void __launch_bounds__(512)
-cfg_sched_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c, const float* __restrict__ latent,
+cfg_sched_kernel(const float* __restrict__ eps_u, const float* __restrict__ eps_c, const float* latent /* may alias out */,
                  const StepCoef* __restrict__ coefs, const int* __restrict__ step_ptr, const float* __restrict__ noise,
                  const float* __restrict__ mask,
                  const float* __restrict__ init_latent, const float* __restrict__ init_noise, int n_per_sample,
-                 float* __restrict__ out, bf16* __restrict__ out_bf16 /* [2B or B][HW][8] */, int B, int dup) {
+                 float* out, bf16* __restrict__ out_bf16 /* [2B or B][HW][8] */, int B, int dup) {
   const int step = step_ptr ? *step_ptr : 0;
   const StepCoef c = coefs[step];
   const int b = blockIdx.x;

@@ -5,7 +5,6 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
-#include <chrono>
 #include <cstring>
 #include <functional>
 
@@ -109,10 +108,6 @@ struct sdtf_engine {
   const char* nccl_path = nullptr;
   sdtf_timings timings{};
   cudaEvent_t ev[4]{};
-  // second stream for the cond half of a CFG step (two half-batch UNet passes in flight; see sdtf_denoise)
-  cudaStream_t st2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  GnScratch gn2;
   // captured step graph
   cudaGraphExec_t graph = nullptr;
   std::string graph_key;
@@ -218,15 +213,6 @@ int sdtf_create(int32_t device, sdtf_engine** out) {
     SDTF_CUDA(cudaMemset(e->gn.counters, 0, sizeof(unsigned) * kGnMaxBatch));
     SDTF_CUDA(cudaMalloc((void**)&e->gn.gens, sizeof(unsigned) * kGnMaxBatch));
     SDTF_CUDA(cudaMemset(e->gn.gens, 0, sizeof(unsigned) * kGnMaxBatch));
-    SDTF_CUDA(cudaStreamCreateWithFlags(&e->st2, cudaStreamNonBlocking));
-    SDTF_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    SDTF_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
-    SDTF_CUDA(cudaMalloc((void**)&e->gn2.partial, sizeof(double) * 64 * kGnMaxBlk * kGnMaxBatch));
-    SDTF_CUDA(cudaMalloc((void**)&e->gn2.counters, sizeof(unsigned) * kGnMaxBatch));
-    SDTF_CUDA(cudaMalloc((void**)&e->gn2.gens, sizeof(unsigned) * kGnMaxBatch));
-    SDTF_CUDA(cudaMalloc((void**)&e->gn2.stats, sizeof(float) * 64 * kGnMaxBatch));
-    SDTF_CUDA(cudaMemset(e->gn2.counters, 0, sizeof(unsigned) * kGnMaxBatch));
-    SDTF_CUDA(cudaMemset(e->gn2.gens, 0, sizeof(unsigned) * kGnMaxBatch));
     SDTF_CUDA(cudaMalloc((void**)&e->step_dev, sizeof(int) * 4));
     for (auto& ev : e->ev) SDTF_CUDA(cudaEventCreate(&ev));
     // kernel attributes are set up-front so that nothing but launches happens under stream capture
@@ -259,14 +245,7 @@ void sdtf_destroy(sdtf_engine* e) {
   cudaFree(e->gn.gens);
   cudaFree(e->gn.stats);
   cudaFree(e->step_dev);
-  cudaFree(e->gn2.partial);
-  cudaFree(e->gn2.counters);
-  cudaFree(e->gn2.gens);
-  cudaFree(e->gn2.stats);
   for (auto& ev : e->ev) cudaEventDestroy(ev);
-  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
-  if (e->ev_join) cudaEventDestroy(e->ev_join);
-  if (e->st2) cudaStreamDestroy(e->st2);
   cudaStreamDestroy(e->st);
   delete e;
 }
@@ -307,6 +286,10 @@ int sdtf_finalize_weights(sdtf_engine* e, const char* component) {
   WeightStore& w = e->weights;
   w.missing.clear();
   e->drop_graph();
+  SDTF_CUDA(cudaStreamSynchronize(e->st));  // nothing may still be reading the weights this call replaces
+  SDTF_CHECK(comp == "unet" || comp == "controlnet" || comp == "vae_decoder" || comp == "vae_encoder" || comp == "text_encoder",
+             "unknown component '" + comp + "' (unet | controlnet | vae_decoder | vae_encoder | text_encoder)");
+  w.begin_component(comp);
   std::vector<std::string> prefixes;
   if (comp == "unet") {
     e->unet = UNetW();
@@ -503,8 +486,64 @@ int sdtf_text_encode(sdtf_engine* e, const DLManagedTensor* tokens, int clip_ski
   e->run_sized([&](Ctx& c) {
     int* d_tok = c.ws->alloc_n<int>((size_t)B * T);
     if (!c.dry) SDTF_CUDA(cudaMemcpyAsync(d_tok, tok.data, tok.bytes(), tok.cuda ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->st));
+    float* x = c.ws->alloc_n<float>((size_t)B * T * kCtxDim);
     float* ctx = c.ws->alloc_n<float>((size_t)out.numel());
-    text_encode(c, e->text, d_tok, B, T, clip_skip, ctx);
+    text_embed(c, e->text, d_tok, nullptr, 0, B, T, x);
+    text_encode(c, e->text, x, B, T, clip_skip, ctx);
+    e->emit(c, ctx, out);
+  });
+  SDTF_CUDA(cudaStreamSynchronize(e->st));
+  SDTF_API_END
+}
+
+int sdtf_text_embed(sdtf_engine* e, const DLManagedTensor* tokens, const DLManagedTensor* positions, DLManagedTensor* out_embedding) {
+  SDTF_API_BEGIN
+  SDTF_CHECK(e->text.ready, "text_encoder weights not finalized");
+  TRef tok = parse(tokens, "tokens", e->device), out = parse(out_embedding, "out_embedding", e->device);
+  SDTF_CHECK(tok.dt == I32, "tokens must be int32");
+  expect_shape(tok, {-1, -1}, "tokens");
+  const int B = (int)tok.shape[0], T = (int)tok.shape[1];
+  SDTF_CHECK(T >= 1 && T <= e->text.max_len, "tokens: sequence longer than the position table");
+  TRef pos;
+  int pos_rows = 0;
+  if (positions) {
+    pos = parse(positions, "positions", e->device);
+    SDTF_CHECK(pos.dt == I32, "positions must be int32");
+    expect_shape(pos, {-1, T}, "positions");
+    pos_rows = (int)pos.shape[0];
+    SDTF_CHECK(pos_rows == 1 || pos_rows == B, "positions must be (1,T) or (B,T)");
+  }
+  expect_shape(out, {B, T, kCtxDim}, "out_embedding");
+  SDTF_CHECK(out.dt == F32, "out_embedding must be float32");
+  e->run_sized([&](Ctx& c) {
+    int* d_tok = c.ws->alloc_n<int>((size_t)B * T);
+    int* d_pos = positions ? c.ws->alloc_n<int>((size_t)pos_rows * T) : nullptr;
+    if (!c.dry) {
+      SDTF_CUDA(cudaMemcpyAsync(d_tok, tok.data, tok.bytes(), tok.cuda ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->st));
+      if (d_pos) SDTF_CUDA(cudaMemcpyAsync(d_pos, pos.data, pos.bytes(), pos.cuda ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->st));
+    }
+    float* x = c.ws->alloc_n<float>((size_t)B * T * kCtxDim);
+    text_embed(c, e->text, d_tok, d_pos, pos_rows, B, T, x);
+    e->emit(c, x, out);
+  });
+  SDTF_CUDA(cudaStreamSynchronize(e->st));
+  SDTF_API_END
+}
+
+int sdtf_text_encode_embedded(sdtf_engine* e, const DLManagedTensor* embedding, int clip_skip, DLManagedTensor* out_context) {
+  SDTF_API_BEGIN
+  SDTF_CHECK(e->text.ready, "text_encoder weights not finalized");
+  TRef emb = parse(embedding, "embedding", e->device), out = parse(out_context, "out_context", e->device);
+  expect_shape(emb, {-1, -1, kCtxDim}, "embedding");
+  const int B = (int)emb.shape[0], T = (int)emb.shape[1];
+  SDTF_CHECK(T >= 1 && T <= 128, "embedding: at most 128 tokens per window (causal attention kernel)");
+  SDTF_CHECK(clip_skip <= -1 && clip_skip >= -kClipLayers, "clip_skip must be in [-12, -1]");
+  expect_shape(out, {B, T, kCtxDim}, "out_context");
+  SDTF_CHECK(out.dt == F32, "out_context must be float32");
+  e->run_sized([&](Ctx& c) {
+    float* x = e->stage_f32(c, emb);
+    float* ctx = c.ws->alloc_n<float>((size_t)out.numel());
+    text_encode(c, e->text, x, B, T, clip_skip, ctx);
     e->emit(c, ctx, out);
   });
   SDTF_CUDA(cudaStreamSynchronize(e->st));
@@ -620,9 +659,14 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
   SDTF_CHECK(d != nullptr, "desc is NULL");
   SDTF_CHECK(e->unet.ready, "unet weights not finalized");
   SDTF_CHECK(d->n_steps >= 1 && d->coefs != nullptr, "n_steps >= 1 and coefs required");
-  const auto t_host0 = std::chrono::steady_clock::now();
-  TRef lat0 = parse(d->latent0, "latent0", e->device), ctx = parse(d->context, "context", e->device);
-  TRef temb = parse(d->t_emb, "t_emb", e->device);
+  // every float input is staged with a plain byte copy into an fp32 buffer: anything but float32 is refused here
+  auto parse_f32 = [&](const DLManagedTensor* t, const char* name) {
+    TRef r = parse(t, name, e->device);
+    SDTF_CHECK(r.dt == F32, std::string(name) + ": must be float32");
+    return r;
+  };
+  TRef lat0 = parse_f32(d->latent0, "latent0"), ctx = parse_f32(d->context, "context");
+  TRef temb = parse_f32(d->t_emb, "t_emb");
   expect_shape(lat0, {-1, -1, -1, 4}, "latent0");
   const int B = (int)lat0.shape[0], h = (int)lat0.shape[1], w = (int)lat0.shape[2], S = d->n_steps;
   SDTF_CHECK(h % 8 == 0 && w % 8 == 0, "latent height/width must be multiples of 8");
@@ -634,19 +678,22 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
   if (split) SDTF_CHECK(cfg && e->comm.active() && e->comm.world == 2, "cfg_split needs guidance > 0 and a 2-rank communicator (sdtf_comm_init)");
   const int srank = split ? e->comm.rank : 0;
   TRef uctx, snoise, mask, initl, initn, hint_img, bimg, bmask, oimg, olat;
-  if (cfg) { uctx = parse(d->uncond_context, "uncond_context", e->device); expect_shape(uctx, {B, T, kCtxDim}, "uncond_context"); }
-  if (d->step_noise) { snoise = parse(d->step_noise, "step_noise", e->device); expect_shape(snoise, {S, B, h, w, 4}, "step_noise"); }
+  // The reference evaluates the two CFG branches as separate model calls (stable_diffusion.py:454-457), so the prompt
+  // and the negative prompt may span different numbers of 77-token windows.
+  if (cfg) { uctx = parse_f32(d->uncond_context, "uncond_context"); expect_shape(uctx, {B, -1, kCtxDim}, "uncond_context"); }
+  const int Tu = cfg ? (int)uctx.shape[1] : T;
+  if (d->step_noise) { snoise = parse_f32(d->step_noise, "step_noise"); expect_shape(snoise, {S, B, h, w, 4}, "step_noise"); }
   const bool inpaint = d->mask != nullptr;
   if (inpaint) {
     SDTF_CHECK(d->init_latent && d->init_noise, "mask needs init_latent and init_noise");
-    mask = parse(d->mask, "mask", e->device); expect_shape(mask, {h, w}, "mask");
-    initl = parse(d->init_latent, "init_latent", e->device); expect_shape(initl, {h, w, 4}, "init_latent");
-    initn = parse(d->init_noise, "init_noise", e->device); expect_shape(initn, {B, h, w, 4}, "init_noise");
+    mask = parse_f32(d->mask, "mask"); expect_shape(mask, {h, w}, "mask");
+    initl = parse_f32(d->init_latent, "init_latent"); expect_shape(initl, {h, w, 4}, "init_latent");
+    initn = parse_f32(d->init_noise, "init_noise"); expect_shape(initn, {B, h, w, 4}, "init_noise");
   }
   const bool control = d->hint_image != nullptr;
   if (control) {
     SDTF_CHECK(e->cnet.ready, "controlnet weights not finalized");
-    hint_img = parse(d->hint_image, "hint_image", e->device); expect_shape(hint_img, {B, 8 * h, 8 * w, 3}, "hint_image");
+    hint_img = parse_f32(d->hint_image, "hint_image"); expect_shape(hint_img, {B, 8 * h, 8 * w, 3}, "hint_image");
   }
   if (d->decode) {
     SDTF_CHECK(e->vdec.ready, "vae_decoder weights not finalized");
@@ -655,19 +702,24 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
     SDTF_CHECK(oimg.dt == U8, "out_images must be uint8");
     if (d->blend_image) {
       SDTF_CHECK(d->blend_mask != nullptr, "blend_image needs blend_mask");
-      bimg = parse(d->blend_image, "blend_image", e->device); expect_shape(bimg, {8 * h, 8 * w, 3}, "blend_image");
-      bmask = parse(d->blend_mask, "blend_mask", e->device); expect_shape(bmask, {8 * h, 8 * w}, "blend_mask");
+      bimg = parse_f32(d->blend_image, "blend_image"); expect_shape(bimg, {8 * h, 8 * w, 3}, "blend_image");
+      bmask = parse_f32(d->blend_mask, "blend_mask"); expect_shape(bmask, {8 * h, 8 * w}, "blend_mask");
     }
   }
-  if (d->out_latent) { olat = parse(d->out_latent, "out_latent", e->device); expect_shape(olat, {B, h, w, 4}, "out_latent"); }
+  if (d->out_latent) { olat = parse_f32(d->out_latent, "out_latent"); expect_shape(olat, {B, h, w, 4}, "out_latent"); }
   std::vector<StepCoef> coefs(S);
   for (int i = 0; i < S; ++i) coefs[i] = to_coef(d->coefs[i]);
-  const int Bt = (cfg && !split) ? 2 * B : B;  // samples per UNet pass on THIS rank
-  const bool dup = cfg && !split;              // uncond | cond halves batched into one pass
+  // How the CFG pair is evaluated on THIS rank:
+  //   dup       one UNet pass over [uncond B | cond B] (equal context lengths; the default)
+  //   two_pass  contexts of different length: one B-sample pass per branch, as the reference's two model calls
+  //   split     2-GPU CFG split: this rank evaluates one branch, the epsilons are all-gathered
+  const bool two_pass = cfg && !split && Tu != T;
+  const bool dup = cfg && !split && !two_pass;
+  const int Bt = dup ? 2 * B : B;  // samples per UNet pass
   const int n = h * w * 4;
-  const std::string key = std::to_string(B) + "x" + std::to_string(h) + "x" + std::to_string(w) + "x" + std::to_string(T) +
-                          (cfg ? (split ? (srank ? "S" : "s") : "c") : "-") + (control ? "n" : "-") + (inpaint ? "m" : "-") + (d->step_noise ? "z" : "-") +
-                          "s" + std::to_string(S);
+  const std::string key = std::to_string(B) + "x" + std::to_string(h) + "x" + std::to_string(w) + "x" + std::to_string(T) + "x" +
+                          std::to_string(Tu) + (cfg ? (split ? (srank ? "S" : "s") : (two_pass ? "t" : "c")) : "-") +
+                          (control ? "n" : "-") + (inpaint ? "m" : "-") + (d->step_noise ? "z" : "-") + "s" + std::to_string(S);
   const bool use_graph = d->use_cuda_graph != 0;
 
   e->run_sized([&](Ctx& c) {
@@ -676,13 +728,11 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
     bf16* lat8 = c.ws->alloc_n<bf16>((size_t)Bt * h * w * 8);
     float* eps = c.ws->alloc_n<float>((size_t)(cfg ? 2 * B : B) * n);  // [uncond B | cond B] (split: gathered from both ranks)
     float* temb_tab = c.ws->alloc_n<float>((size_t)S * 320);
-    float* temb_in = c.ws->alloc_n<float>((size_t)Bt * 320);
     StepCoef* d_coefs = c.ws->alloc_n<StepCoef>(S);
     float* d_snoise = d->step_noise ? c.ws->alloc_n<float>((size_t)S * B * n) : nullptr;
     float* d_mask = inpaint ? c.ws->alloc_n<float>((size_t)h * w) : nullptr;
     float* d_initl = inpaint ? c.ws->alloc_n<float>((size_t)n) : nullptr;
     float* d_initn = inpaint ? c.ws->alloc_n<float>((size_t)B * n) : nullptr;
-    bf16* ctxb = c.ws->alloc_n<bf16>((size_t)Bt * T * kCtxDim);
     View hint;
     View ctrl[13];
     static const int lv[13] = {0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 3};
@@ -691,7 +741,6 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
       hint = c.alloc_view(Bt, h, w, 320);
       for (int i = 0; i < 13; ++i) ctrl[i] = c.alloc_view(Bt, h >> lv[i], w >> lv[i], ch[i]);
     }
-    CtxKV kv, kv_cn;
     auto copy_in = [&](void* dst, const TRef& t) {
       if (!c.dry) SDTF_CUDA(cudaMemcpyAsync(dst, t.data, t.bytes(), t.cuda ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->st));
     };
@@ -702,23 +751,36 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
     if (d_snoise) copy_in(d_snoise, snoise);
     if (inpaint) { copy_in(d_mask, mask); copy_in(d_initl, initl); copy_in(d_initn, initn); }
     c.memset0(e->step_dev, sizeof(int));
-    {
-      // contexts -> bf16 [uncond B | cond B], K/V projections hoisted out of the step loop
+
+    // ---- UNet passes of one step: contexts -> bf16, K/V projections hoisted out of the step loop ----
+    struct Pass {
+      int T = 0;
+      size_t eps_off = 0;
+      CtxKV kv, kv_cn;
+    };
+    std::vector<Pass> passes;
+    auto add_pass = [&](const TRef* first, const TRef* second, int Tp, size_t eps_off) {
+      Pass ps;
+      ps.T = Tp; ps.eps_off = eps_off;
+      bf16* ctxb = c.ws->alloc_n<bf16>((size_t)Bt * Tp * kCtxDim);
       const size_t m = c.ws->mark();
-      float* f = c.ws->alloc_n<float>((size_t)B * T * kCtxDim);
-      if (cfg && (!split || srank == 0)) {
-        copy_in(f, uctx);
-        c.cast_pad(f, (long long)B * T, kCtxDim, kCtxDim, 1.f, ctxb, false);
-      }
-      if (!split || srank == 1) {
-        copy_in(f, ctx);
-        c.cast_pad(f, (long long)B * T, kCtxDim, kCtxDim, 1.f, ctxb + (dup ? (size_t)B * T * kCtxDim : 0), false);
+      float* f = c.ws->alloc_n<float>((size_t)B * Tp * kCtxDim);
+      copy_in(f, *first);
+      c.cast_pad(f, (long long)B * Tp, kCtxDim, kCtxDim, 1.f, ctxb, false);
+      if (second) {
+        copy_in(f, *second);
+        c.cast_pad(f, (long long)B * Tp, kCtxDim, kCtxDim, 1.f, ctxb + (size_t)B * Tp * kCtxDim, false);
       }
       c.ws->release(m);
-    }
-    project_context(c, ctxb, Bt, T, unet_attn_layers(e->unet), kv);
+      project_context(c, ctxb, Bt, Tp, unet_attn_layers(e->unet), ps.kv);
+      if (control) project_context(c, ctxb, Bt, Tp, encoder_attn_layers(e->cnet.enc), ps.kv_cn);
+      passes.push_back(std::move(ps));
+    };
+    if (dup) add_pass(&uctx, &ctx, T, 0);
+    else if (two_pass) { add_pass(&uctx, nullptr, Tu, 0); add_pass(&ctx, nullptr, T, (size_t)B * n); }
+    else if (split) { if (srank == 0) add_pass(&uctx, nullptr, Tu, 0); else add_pass(&ctx, nullptr, T, (size_t)B * n); }
+    else add_pass(&ctx, nullptr, T, 0);
     if (control) {
-      project_context(c, ctxb, Bt, T, encoder_attn_layers(e->cnet.enc), kv_cn);
       const size_t m = c.ws->mark();
       const int H = 8 * h, W = 8 * w;
       float* f = c.ws->alloc_n<float>((size_t)B * H * W * 3);
@@ -736,76 +798,30 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
     const float* tab_all_c = control ? time_table(c, e->cnet.enc.time, temb_tab, S) : nullptr;
     float* tab_u = c.ws->alloc_n<float>((size_t)Bt * ncat_u);
     float* tab_c = control ? c.ws->alloc_n<float>((size_t)Bt * ncat_c) : nullptr;
-    (void)temb_in;
-
-    // Two half-batch UNet passes in flight (SDTF_DUAL=1; default OFF): with guidance the step evaluates [uncond B | cond B];
-    // the two halves are independent, so the cond half runs on a second stream with its own workspace slice and
-    // GroupNorm scratch.  Persistent kernels of one half fill the SMs the other half's kernel leaves idle in its last,
-    // partial wave (256 tile units on 74 CTA-pair slots = 3.46 waves at the 64x64 level) and while its small kernels
-    // sit in launch / barrier latencies.  Results are bit-identical to the single 2B pass (a sample's result does not
-    // depend on its batch).  Not used with ControlNet, the 2-GPU CFG split, or operator tracing.
-    // Measured on B200 at batch 8 + 8 (tools/ab_env.sh, same box, alternating): 18.49 / 18.41 ms per step against
-    // 17.81 / 17.80 ms for the single batch-16 pass — the half-size kernels lose more (weights streamed twice, half the
-    // tiles per launch) than the overlap recovers under the power cap.  Kept as a switch, off.
-    static const int dual_env = getenv("SDTF_DUAL") ? atoi(getenv("SDTF_DUAL")) : 0;
-    const bool dual = dual_env && dup && !control && !split && !trace_on();
-    CtxKV kv_hi;  // K|V of the cond half: same layers, pointers advanced by B samples
-    size_t half_bytes = 0;
-    if (dual) {
-      const auto layers = unet_attn_layers(e->unet);
-      kv_hi.T = kv.T;
-      for (size_t l = 0; l < kv.kv.size(); ++l) kv_hi.kv.push_back(kv.kv[l] + (size_t)B * T * 2 * layers[l]->hs);
-      Arena probe;  // workspace a half pass needs: a dry walk of the same graph code
-      probe.dry = true;
-      Ctx cp = c;
-      cp.ws = &probe; cp.dry = true;
-      unet_forward(cp, e->unet, lat8, B, h, w, nullptr, kv, nullptr, eps, tab_u);
-      half_bytes = probe.peak + 4096;
-    }
 
     // ---- one denoising step ----
+    // (Two half-batch passes in flight on two streams were measured and rejected in round 1: 18.45 ms per step against
+    // 17.80 ms for the single 2B pass, profiles/r01_i_dual_stream_ab.log.)
     auto step = [&](Ctx& sc) {
       ++sc.launches;
       if (!sc.dry) {
         temb_select_kernel<<<ceil_div(Bt * ncat_u, 256), 256, 0, e->st>>>(tab_all_u, e->step_dev, ncat_u, Bt, tab_u);
         SDTF_CUDA(cudaGetLastError());
       }
-      const bf16* cptr[13];
       if (control) {
         ++sc.launches;
         if (!sc.dry) {
           temb_select_kernel<<<ceil_div(Bt * ncat_c, 256), 256, 0, e->st>>>(tab_all_c, e->step_dev, ncat_c, Bt, tab_c);
           SDTF_CUDA(cudaGetLastError());
         }
-        controlnet_forward(sc, e->cnet, lat8, Bt, h, w, nullptr, kv_cn, hint, ctrl, tab_c);
-        for (int i = 0; i < 13; ++i) cptr[i] = ctrl[i].p;
       }
-      if (dual) {
-        const size_t m_dual = sc.ws->mark();
-        Arena sub;  // the cond half's slice of the workspace
-        sub.base = reinterpret_cast<uint8_t*>(sc.ws->alloc(half_bytes));
-        sub.cap = half_bytes; sub.dry = sc.dry;
-        Ctx c2 = sc;
-        c2.st = e->st2; c2.ws = &sub; c2.gn = e->gn2; c2.launches = 0;
-        c2.gn.share = 2;
-        GnScratch g1 = sc.gn;
-        sc.gn.share = 2;
-        if (!sc.dry) {
-          SDTF_CUDA(cudaEventRecord(e->ev_fork, e->st));
-          SDTF_CUDA(cudaStreamWaitEvent(e->st2, e->ev_fork, 0));
+      for (Pass& ps : passes) {
+        const bf16* cptr[13];
+        if (control) {
+          controlnet_forward(sc, e->cnet, lat8, Bt, h, w, nullptr, ps.kv_cn, hint, ctrl, tab_c);
+          for (int i = 0; i < 13; ++i) cptr[i] = ctrl[i].p;
         }
-        unet_forward(sc, e->unet, lat8, B, h, w, nullptr, kv, nullptr, eps, tab_u);
-        unet_forward(c2, e->unet, lat8 + (size_t)B * h * w * 8, B, h, w, nullptr, kv_hi, nullptr, eps + (size_t)B * n,
-                     tab_u + (size_t)B * ncat_u);
-        if (!sc.dry) {
-          SDTF_CUDA(cudaEventRecord(e->ev_join, e->st2));
-          SDTF_CUDA(cudaStreamWaitEvent(e->st, e->ev_join, 0));
-        }
-        sc.gn = g1;
-        sc.launches += c2.launches;
-        sc.ws->release(m_dual);
-      } else {
-        unet_forward(sc, e->unet, lat8, Bt, h, w, nullptr, kv, control ? cptr : nullptr, eps + (split ? (size_t)srank * B * n : 0), tab_u);
+        unet_forward(sc, e->unet, lat8, Bt, h, w, nullptr, ps.kv, control ? cptr : nullptr, eps + ps.eps_off, tab_u);
       }
       if (split) {  // C1: in-place all-gather of this rank's branch; both ranks then run the update redundantly
         ++sc.launches;
@@ -823,13 +839,20 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
         SDTF_CUDA(cudaGetLastError());
       }
     };
+    // stable_diffusion.py:476-478: `callback(iteration)` after every iteration.  The callback runs on the calling
+    // thread once the step has finished on the device (one stream synchronisation per step, only when requested).
+    auto after_step = [&](int s) {
+      if (!d->on_step) return;
+      SDTF_CUDA(cudaStreamSynchronize(e->st));
+      d->on_step(s + 1, d->on_step_user);
+    };
 
     if (!c.dry) SDTF_CUDA(cudaEventRecord(e->ev[1], e->st));
     const size_t m_loop = c.ws->mark();
     if (c.dry) {
       step(c);
     } else if (!use_graph) {
-      for (int s = 0; s < S; ++s) step(c);
+      for (int s = 0; s < S; ++s) { step(c); after_step(s); }
     } else {
       const std::string gkey = key + "@" + std::to_string((uintptr_t)e->ws.base);
       if (!e->graph || e->graph_key != gkey) {
@@ -851,7 +874,7 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
         e->graph_key = gkey;
         e->graph_launches = gc.launches;
       }
-      for (int s = 0; s < S; ++s) SDTF_CUDA(cudaGraphLaunch(e->graph, e->st));
+      for (int s = 0; s < S; ++s) { SDTF_CUDA(cudaGraphLaunch(e->graph, e->st)); after_step(s); }
       c.launches += e->graph_launches * S;
     }
     c.ws->release(m_loop);
@@ -885,7 +908,6 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
   cudaEventElapsedTime(&ms, e->ev[1], e->ev[2]); e->timings.loop_ms = ms;
   cudaEventElapsedTime(&ms, e->ev[2], e->ev[3]); e->timings.decode_ms = ms;
   cudaEventElapsedTime(&ms, e->ev[0], e->ev[3]); e->timings.total_ms = ms;
-  (void)t_host0;
   SDTF_API_END
 }
 

@@ -87,20 +87,25 @@ class Engine:
         self._check(self._lib.sdtf_finalize_weights(self._h, component.encode()))
         self.loaded.add(component)
 
-    def load_file(self, path: str, component: str):
-        """.safetensors or torch pickle, as the reference's loader accepts (ckpt_loader.py:2139-2145)."""
+    @staticmethod
+    def read_checkpoint(path: str) -> dict:
+        """.safetensors or torch pickle (.ckpt / .pth, optionally wrapped in {"state_dict": ...}) -> {key: tensor}, as the
+        reference's loader reads them (ckpt_loader.py:2139-2145)."""
         if path.endswith(".safetensors"):
             from safetensors import safe_open
             sd = {}
             with safe_open(path, framework="pt", device="cpu") as f:
                 for k in f.keys():
                     sd[k] = f.get_tensor(k)
-        else:
-            import torch
-            sd = torch.load(path, map_location="cpu")
-            if "state_dict" in sd:
-                sd = sd["state_dict"]
-        self.load_state_dict(sd, component)
+            return sd
+        import torch
+        sd = torch.load(path, map_location="cpu")
+        if "state_dict" in sd:
+            sd = sd["state_dict"]
+        return sd
+
+    def load_file(self, path: str, component: str):
+        self.load_state_dict(self.read_checkpoint(path), component)
 
     # ------------------------------------------------------------------------------------------------ helpers
     @staticmethod
@@ -172,13 +177,37 @@ class Engine:
 
     def text_encode(self, tokens, clip_skip: int = -1):
         """TextEncoder(TextClipEmbedding([tokens, positions])) (text_encoder.py:106-135): int tokens (B,T<=77) ->
-        context (B,T,768) float32 (NumPy)."""
-        tokens = np.ascontiguousarray(np.asarray(tokens, dtype=np.int32))
+        context (B,T,768) float32 (NumPy).  A float (B,T,768) input is taken as the output of `text_embed` (possibly
+        with textual-inversion vectors spliced in) and goes through TextEncoder only (text_encoder.py:125-135)."""
+        arr = np.asarray(tokens)
+        if np.issubdtype(arr.dtype, np.floating):
+            emb = np.ascontiguousarray(arr, dtype=np.float32)
+            if emb.ndim == 2:
+                emb = emb[None]
+            out = np.empty(emb.shape, np.float32)
+            dl = _lib.DL()
+            self._check(self._lib.sdtf_text_encode_embedded(self._h, dl(emb), int(clip_skip), dl(out)))
+            return out
+        tokens = np.ascontiguousarray(arr, dtype=np.int32)
         if tokens.ndim == 1:
             tokens = tokens[None]
         out = np.empty(tokens.shape + (768,), np.float32)
         dl = _lib.DL()
         self._check(self._lib.sdtf_text_encode(self._h, dl(tokens), int(clip_skip), dl(out)))
+        return out
+
+    def text_embed(self, tokens, positions=None):
+        """TextClipEmbedding.predict_on_batch([tokens, positions]) (text_encoder.py:22-33,106-122) -> (B,T,768) float32."""
+        tokens = np.ascontiguousarray(np.asarray(tokens, dtype=np.int32))
+        if tokens.ndim == 1:
+            tokens = tokens[None]
+        if positions is not None:
+            positions = np.ascontiguousarray(np.asarray(positions, dtype=np.int32))
+            if positions.ndim == 1:
+                positions = positions[None]
+        out = np.empty(tokens.shape + (768,), np.float32)
+        dl = _lib.DL()
+        self._check(self._lib.sdtf_text_embed(self._h, dl(tokens), dl(positions), dl(out)))
         return out
 
     def cfg_sched_step(self, eps_u, eps_c, latent_prev, coef, noise=None, mask=None, init_latent=None, init_noise=None):
@@ -222,9 +251,9 @@ class Engine:
 
     def denoise(self, latent0, context, uncond_context, t_emb, coefs, step_noise=None, mask=None, init_latent=None,
                 init_noise=None, hint_image=None, blend_image=None, blend_mask=None, decode=True, use_cuda_graph=True,
-                return_latent=False, cfg_split=False):
+                return_latent=False, cfg_split=False, callback=None):
         """The whole loop of generate_image (stable_diffusion.py:442-486) in one call.  coefs: list of StepCoef in
-        execution order; t_emb (n_steps, 320)."""
+        execution order; t_emb (n_steps, 320).  callback(iteration): called after every step (:476-478)."""
         latent0 = self._f32(latent0)
         B, h, w, _ = latent0.shape
         n = len(coefs)
@@ -249,7 +278,20 @@ class Engine:
         lat = self._like(latent0, (B, h, w, 4)) if (return_latent or not decode) else None
         d.out_images = dl(images)
         d.out_latent = dl(lat)
+        raised = []
+        if callback is not None:
+            def _on_step(iteration, _user):
+                if raised:
+                    return
+                try:
+                    callback(int(iteration))
+                except BaseException as ex:  # an exception cannot unwind through the C frames: re-raised after the call
+                    raised.append(ex)
+            cb = _lib.ON_STEP(_on_step)
+            d.on_step = ctypes.cast(cb, ctypes.c_void_p)
         self._check(self._lib.sdtf_denoise(self._h, ctypes.byref(d)))
+        if raised:
+            raise raised[0]
         if decode and return_latent:
             return images, lat
         return images if decode else lat

@@ -34,7 +34,8 @@ class Scheduler:
         self.num_inference_steps = None
         self.timesteps = np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int32)
         self._step_index = None
-        self._engine = None
+        self.engine = None   # set by the pipeline that owns this scheduler; `step` creates one on `device` otherwise
+        self.device = 0
 
     # ------------------------------------------------------------------------------------------ schedules
     def set_timesteps(self, num_inference_steps: int):
@@ -101,9 +102,9 @@ class Scheduler:
         """Drop-in for Scheduler.step(eps, t, latent_prev) (scheduler.py:246-315).  Runs the fused kernel."""
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
-        if self._engine is None:
+        if self.engine is None:
             from .engine import Engine
-            self._engine = Engine(0)
+            self.engine = Engine(self.device)
         if self._step_index is None:
             self._step_index = self._index_of(timestep)
         ca, cb, cn = self.step_scalars(int(timestep), eta)
@@ -111,7 +112,7 @@ class Scheduler:
         if cn != 0.0:
             noise = np.random.randn(*np.shape(latent)).astype(np.float32)  # global NumPy RNG, as scheduler.py:301
         coef = StepCoef(0.0, 0.0, ca, cb, cn, 0.0, 0.0)
-        out = self._engine.cfg_sched_step(None, latent, latent_prev, coef, noise=noise)
+        out = self.engine.cfg_sched_step(None, latent, latent_prev, coef, noise=noise)
         self._step_index += 1
         return out
 

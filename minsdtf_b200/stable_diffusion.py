@@ -10,9 +10,11 @@ Different by design: the loop body (2 UNet calls (+2 ControlNet calls) + CFG + s
 and the decode (:482-486) run on the GPU inside one `sdtf_denoise` call; cond and uncond are batched into one UNet
 pass; cross-attention K/V and HintNet features are computed once per image.
 
-Out of scope this round: the CLIP text tower / tokenizer.  `encode_text` therefore needs a
-user-supplied `text_encoder_fn`; `generate_image(encoded_text, ...)` — the reference's own lower-level entry — is
-fully supported, as are precomputed embeddings passed as `prompt`.
+Text side: the CLIP text tower runs on the engine (`text_clip_embedding` / `text_encoder` models, as the
+reference splits it); string prompts go through `prompt_weighting.weighted_text_embeddings` — `(word:1.3)` attention
+syntax, up to four 75-token windows, mean-preserving re-weighting, textual-inversion vectors — with a CLIP BPE tokenizer
+built from a local vocabulary file (the reference downloads it; `bpe_vocab=` / $SDTF_BPE_VOCAB / the Keras cache path).
+LoRA files are merged into the checkpoint tensors at load time (`lora.py`).
 """
 from __future__ import annotations
 
@@ -20,6 +22,7 @@ import os
 
 import numpy as np
 
+from . import lora as _lora, prompt_weighting as _pw
 from .engine import Engine
 from .scheduler import Scheduler, timestep_embedding
 
@@ -78,33 +81,49 @@ class StableDiffusionBase:
                                    inpaint_mask=inpaint_mask, mask_blur_strength=mask_blur_strength,
                                    guidance_rescale=guidance_rescale, callback=callback)
 
+    def load_embedding(self, embedding_path):
+        """Textual-inversion file -> (n_vectors, 768) array, or None (stable_diffusion.py:71-82): a torch pickle whose
+        `string_to_param` dict holds the learned vectors (the last float entry wins, as in the reference)."""
+        embedding = None
+        if os.path.exists(str(embedding_path)):
+            import torch
+            state = torch.load(embedding_path, map_location="cpu")
+            params = state.get("string_to_param") if hasattr(state, "get") else None
+            if params is not None:
+                for value in params.values():
+                    if value.dtype in (torch.float32, torch.float16):
+                        embedding = value.detach().float().numpy()
+        return embedding
+
     def encode_text(self, prompt, embedding_data=None):
-        """Reference: tokenizer -> TextClipEmbedding -> TextEncoder (:176-215).  Accepted here:
-        * a float array (T,768) / (B,T,768): already-encoded text, passed through;
-        * an integer array of CLIP token ids (T,) / (B,T<=77): encoded by the engine's text tower (`clip_skip` as given
-          to the constructor);
-        * a string: tokenised by `model.tokenizer` (any object with `.encode(str) -> ids`; the BPE vocabulary is a
-          download in the reference, clip_tokenizer.py:79-82, and is not available offline), padded with 49407 to 77.
-        Long-prompt weighting and textual-inversion embeddings (`embedding_data`) are host-side features outside the
-        hot path."""
-        if embedding_data is not None:
-            raise NotImplementedError("textual-inversion embeddings are outside the hot path (SURVEY.md §2)")
+        """Prompt -> context (stable_diffusion.py:176-215).
+        * a string (or list of strings): tokenised by `self.tokenizer`, attention syntax `(word:1.3)` / `[word]` parsed,
+          up to 4 windows of 75 tokens each encoded on its own -> (B, 77 m, 768), weighted with the mean preserved
+          (long_prompt_weighting.py:240-333);
+        * `embedding_data`: path of a textual-inversion file (or, beyond the reference, an (n,768) array): n placeholder
+          tokens are put in front of the prompt and their embedding rows replaced by the learned vectors (:202-209);
+        * beyond the reference: a float array (T,768) / (B,T,768) is passed through as an already-encoded prompt, an
+          integer array (T,) / (B,T<=77 or 77 m) is taken as CLIP token ids."""
         if isinstance(prompt, np.ndarray) and np.issubdtype(prompt.dtype, np.floating):
             return prompt.astype(np.float32)
-        if isinstance(prompt, str):
-            tok = getattr(self, "tokenizer", None)
-            if tok is None:
-                fn = getattr(self, "text_encoder_fn", None)
-                if fn is not None:
-                    return np.asarray(fn(prompt), dtype=np.float32)
-                raise NotImplementedError(
-                    "no tokenizer: the CLIP BPE vocabulary cannot be downloaded offline — set `model.tokenizer` (an object with "
-                    ".encode(str) -> token ids), or pass token ids / an encoded (T,768) array as `prompt`")
-            ids = list(tok.encode(prompt))
-            if len(ids) > MAX_PROMPT_LENGTH:  # as the reference's tokenizer path: truncate, keep the end token
-                ids = ids[:MAX_PROMPT_LENGTH - 1] + [49407]
-            ids = ids + [49407] * (MAX_PROMPT_LENGTH - len(ids))
-            prompt = np.asarray(ids, np.int32)
+        if isinstance(prompt, str) or (isinstance(prompt, (list, tuple)) and prompt and isinstance(prompt[0], str)):
+            embedding, count = None, 0
+            if embedding_data is not None:
+                if isinstance(embedding_data, str):
+                    embedding = self.load_embedding(embedding_data)
+                    if embedding is None:
+                        raise ValueError(f"failed to load embedding file: {embedding_data}.")
+                elif isinstance(embedding_data, np.ndarray):
+                    embedding = np.asarray(embedding_data, np.float32)
+                if embedding is not None:
+                    count = embedding.shape[0]
+                    embedding = embedding[None]
+            fn = getattr(self, "text_encoder_fn", None)
+            if fn is not None and getattr(self, "_tokenizer", None) is None and embedding is None:
+                return np.asarray(fn(prompt), dtype=np.float32)  # user-supplied text encoder
+            return _pw.weighted_text_embeddings(self.tokenizer, self.text_clip_embedding.predict_on_batch,
+                                                self.text_encoder.predict_on_batch, prompt, pad_token_id=49407,
+                                                embedding=embedding, embedding_tokens_count=count)
         tokens = np.asarray(prompt)
         if not np.issubdtype(tokens.dtype, np.integer):
             raise TypeError("encode_text: expected a string, integer token ids or an encoded float array")
@@ -112,6 +131,28 @@ class StableDiffusionBase:
 
     def _encode_tokens(self, tokens):
         raise NotImplementedError("token ids need the engine-backed StableDiffusion class")
+
+    @property
+    def tokenizer(self):
+        """CLIP BPE tokenizer (the reference's property, stable_diffusion.py:522-531, builds SimpleTokenizer() from a
+        downloaded vocabulary).  Here the vocabulary file must be local: `bpe_vocab=` of the constructor,
+        $SDTF_BPE_VOCAB, or where Keras would have cached the download."""
+        if getattr(self, "_tokenizer", None) is None:
+            from .bpe import ClipBPE
+            cands = [getattr(self, "bpe_vocab", None), os.environ.get("SDTF_BPE_VOCAB"),
+                     os.path.expanduser("~/.keras/datasets/bpe_simple_vocab_16e6.txt.gz")]
+            path = next((c for c in cands if c and os.path.exists(str(c))), None)
+            if path is None:
+                raise FileNotFoundError(
+                    "no CLIP BPE vocabulary: the reference downloads bpe_simple_vocab_16e6.txt.gz (clip_tokenizer.py:79-82), "
+                    "which is impossible offline — pass bpe_vocab=<path>, set $SDTF_BPE_VOCAB, assign `model.tokenizer`, or "
+                    "pass token ids / an encoded (T,768) array as `prompt`")
+            self._tokenizer = ClipBPE(str(path))
+        return self._tokenizer
+
+    @tokenizer.setter
+    def tokenizer(self, tok):
+        self._tokenizer = tok
 
     # ---------------------------------------------------------------------------------- host-side preprocessing
     def gaussian_blur(self, image, radius=3, h_axis=1, v_axis=2):
@@ -184,6 +225,8 @@ class StableDiffusionBase:
         if diffusion_noise is not None and seed is not None:
             raise ValueError("`diffusion_noise` and `seed` should not both be passed to `generate_image`. `seed` is only "
                              "used to generate diffusion noise when it's not already user-specified.")
+        if cfg_split and diffusion_noise is None and seed is None:
+            raise ValueError("cfg_split: both GPUs of a pair must start from the same latent — pass `seed` or `diffusion_noise`")
         context = self._expand_tensor(encoded_text, batch_size)
         uncond = None
         if unconditional_guidance_scale > 0.0:
@@ -192,17 +235,9 @@ class StableDiffusionBase:
             else:
                 uncond = self._expand_tensor(self.encode_text("" if negative_prompt is None else negative_prompt,
                                                               negative_embedding), batch_size)
-            # long prompts: both contexts must span the same number of 77-token windows; the shorter one is continued
-            # with empty-prompt windows, as the reference pads it (long_prompt_weighting.py)
-            tc, tu = context.shape[1], uncond.shape[1]
-            if tc != tu:
-                if tc % MAX_PROMPT_LENGTH or tu % MAX_PROMPT_LENGTH:
-                    raise ValueError(f"context lengths {tc} and {tu} differ and are not multiples of 77")
-                empty = np.repeat(self._get_unconditional_context(), batch_size, axis=0)
-                if tu < tc:
-                    uncond = np.concatenate([uncond] + [empty] * ((tc - tu) // MAX_PROMPT_LENGTH), axis=1)
-                else:
-                    context = np.concatenate([context] + [empty] * ((tu - tc) // MAX_PROMPT_LENGTH), axis=1)
+            # cond and uncond may span different numbers of 77-token windows (a long prompt against the empty negative
+            # prompt): the reference evaluates the two branches as separate model calls (:454-457), and so does the
+            # engine then (two B-sample passes per step instead of one 2B pass)
         if diffusion_noise is not None:
             diffusion_noise = np.squeeze(diffusion_noise)
             if diffusion_noise.ndim == 3:
@@ -241,9 +276,12 @@ class StableDiffusionBase:
         step_noise = None
         if any(c.cn != 0.0 for c in coefs):  # TCD: one global-RNG draw per non-final step (scheduler.py:301)
             step_noise = np.zeros((len(exec_ts),) + latent0.shape, np.float32)
+            # with the CFG split both members of a pair must draw the same noise: a generator seeded by `seed` replaces
+            # the process-global one there
+            draw = np.random.RandomState(0 if seed is None else seed).randn if cfg_split else np.random.randn
             for i, c in enumerate(coefs):
                 if c.cn != 0.0:
-                    step_noise[i] = np.random.randn(*latent0.shape).astype(np.float32)
+                    step_noise[i] = draw(*latent0.shape).astype(np.float32)
         inpainting = latent_mask is not None and init_latent is not None
         blend = input_mask_array is not None and input_image_array is not None
         out = self.engine.denoise(
@@ -253,9 +291,7 @@ class StableDiffusionBase:
             init_noise=noise if inpainting else None, hint_image=hint_image,
             blend_image=input_image_array[0] if blend else None,
             blend_mask=input_mask_array[0, ..., 0] if blend else None,
-            decode=True, use_cuda_graph=use_cuda_graph, return_latent=return_latent, cfg_split=cfg_split)
-        if callback is not None:
-            callback(len(exec_ts))
+            decode=True, use_cuda_graph=use_cuda_graph, return_latent=return_latent, cfg_split=cfg_split, callback=callback)
         return out
 
     # ---------------------------------------------------------------------------------- helpers (reference names)
@@ -301,11 +337,12 @@ class StableDiffusionBase:
 class StableDiffusion(StableDiffusionBase):
     """Reference constructor (stable_diffusion.py:620-631).  `*_ckpt` may be a path (.safetensors / torch pickle in
     the reference's key convention) or an in-memory state dict.  Without real checkpoints offline, `synthetic=True`
-    builds seeded random-init SD1.5 weights (minsdtf_b200.synth)."""
+    builds seeded random-init SD1.5 weights (minsdtf_b200.synth).  `lora_path`: kohya-format LoRA file (or its state
+    dict), merged into the UNet / text-encoder tensors before they are packed (ckpt_loader.py:2169-2180, 2196-2276)."""
 
     def __init__(self, img_height=512, img_width=512, jit_compile=False, clip_skip=-1, unet_ckpt=None,
                  text_encoder_ckpt=None, vae_ckpt=None, lora_path=None, controlnet_path=None, active_tcd=False,
-                 device=0, synthetic=False, engine=None):
+                 device=0, synthetic=False, engine=None, bpe_vocab=None):
         super().__init__(img_height, img_width, jit_compile, active_tcd)
         self.clip_skip = clip_skip
         self.unet_ckpt = unet_ckpt
@@ -313,22 +350,30 @@ class StableDiffusion(StableDiffusionBase):
         self.vae_ckpt = vae_ckpt
         self.controlnet_path = controlnet_path
         self.lora_path = None
-        if lora_path is not None:
-            raise NotImplementedError("LoRA merging is load-time host math outside this round's scope (SURVEY.md §2)")
+        self.text_encoder_lora_dict = None
+        self.unet_lora_dict = None
+        if isinstance(lora_path, dict) or os.path.exists(str(lora_path)):  # a missing file is ignored, as the reference does (:642)
+            self.text_encoder_lora_dict, self.unet_lora_dict = _lora.load_lora(lora_path)
+            self.lora_path = lora_path
         self.synthetic = synthetic
         self.device = device
+        self.bpe_vocab = bpe_vocab
         self._engine = engine
         self._models = {}
+        self._loaded_here = set()
+        self.scheduler.device = device
 
     @property
     def engine(self) -> Engine:
         if self._engine is None:
             self._engine = Engine(self.device)
+        self.scheduler.engine = self._engine  # Scheduler.step (the reference's per-call API) runs on the same engine
         return self._engine
 
     def _ensure(self, component, src):
         eng = self.engine
-        if component in eng.loaded:
+        deltas = {"unet": self.unet_lora_dict, "text_encoder": self.text_encoder_lora_dict}.get(component)
+        if component in eng.loaded and (not deltas or component in self._loaded_here):
             return
         if src is None:
             if not self.synthetic:
@@ -340,9 +385,15 @@ class StableDiffusion(StableDiffusionBase):
                    "text_encoder": lambda: synth.make_state_dict("text_encoder"),
                    "controlnet": synth.make_controlnet_state_dict}[component]()
         if isinstance(src, (str, os.PathLike)):
-            eng.load_file(str(src), component)
-        else:
-            eng.load_state_dict(src, component)
+            src = eng.read_checkpoint(str(src))
+        if deltas:
+            from . import keys as K
+            src, n, unused = _lora.merge(src, deltas, K.unet_alias_map() if component == "unet" else None)
+            print(f"Apply {n}/{len(deltas)} lora weights" if unused else f"Apply {n} lora weights")
+            if unused:
+                print(f"Failed to apply lora list: {unused}")
+        eng.load_state_dict(src, component)
+        self._loaded_here.add(component)
 
     def load_all(self, control=False, encoder=False):
         self._ensure("unet", self.unet_ckpt)
@@ -378,19 +429,18 @@ class StableDiffusion(StableDiffusionBase):
         self._ensure("controlnet", self.controlnet_path)
         return _Model(lambda x: self.engine.controlnet(x[0], x[1], x[2], x[3]))
 
-    # The reference splits the text tower into two Keras models, TextClipEmbedding([tokens, positions]) -> (B,77,768)
-    # and TextEncoder(embedding) (:700-725); the engine runs embedding lookup and the 12 layers in one call, so the
-    # first shim only carries the token ids to the second (the pair composes exactly like the reference's:
-    # `text_encoder.predict_on_batch(text_clip_embedding.predict_on_batch([tokens, positions]))`).
+    # The reference's two text models (:674-690, 700-725): TextClipEmbedding([tokens, positions]) -> (B,77,768) embeddings
+    # and TextEncoder(embeddings) -> context.  Both are engine entry points (sdtf_text_embed, sdtf_text_encode_embedded),
+    # so textual-inversion vectors can be spliced in between exactly as long_prompt_weighting.py:202-209 does.
     @property
     def text_clip_embedding(self):
         self._ensure("text_encoder", self.text_encoder_ckpt)
-        return _Model(lambda x: np.asarray(x[0], np.int32))
+        return _Model(lambda x: self.engine.text_embed(x[0], x[1] if len(x) > 1 else None))
 
     @property
     def text_encoder(self):
         self._ensure("text_encoder", self.text_encoder_ckpt)
-        return _Model(lambda tokens: self.engine.text_encode(tokens, self.clip_skip))
+        return _Model(lambda emb: self.engine.text_encode(emb, self.clip_skip))
 
     def _encode_tokens(self, tokens):
         """(T,) / (B,T) token ids -> (T,768) / (B,T,768).  T > 77 must be a multiple of 77: each 77-token window is
@@ -410,9 +460,20 @@ class StableDiffusion(StableDiffusionBase):
             out = self.engine.text_encode(tok2, self.clip_skip)
         return out[0] if one else out
 
-    def generate_image(self, encoded_text, **kw):
+    def generate_image(self, encoded_text, negative_prompt=None, batch_size=1, num_steps=50, unconditional_guidance_scale=7.5,
+                       diffusion_noise=None, seed=None, negative_embedding=None, control_net_image=None, inpaint_mask=None,
+                       mask_blur_strength=None, reference_image=None, reference_image_strength=0.8, guidance_rescale=0.0,
+                       callback=None, **engine_options):
+        """Same positional signature as the reference (stable_diffusion.py:317-334); `engine_options`: return_latent,
+        use_cuda_graph, cfg_split."""
         self._ensure("unet", self.unet_ckpt)
         self._ensure("vae_decoder", self.vae_ckpt)
-        if kw.get("control_net_image") is not None:
+        if control_net_image is not None:
             self._ensure("controlnet", self.controlnet_path)
-        return super().generate_image(encoded_text, **kw)
+        return super().generate_image(
+            encoded_text, negative_prompt=negative_prompt, batch_size=batch_size, num_steps=num_steps,
+            unconditional_guidance_scale=unconditional_guidance_scale, diffusion_noise=diffusion_noise, seed=seed,
+            negative_embedding=negative_embedding, control_net_image=control_net_image, inpaint_mask=inpaint_mask,
+            mask_blur_strength=mask_blur_strength, reference_image=reference_image,
+            reference_image_strength=reference_image_strength, guidance_rescale=guidance_rescale, callback=callback,
+            **engine_options)

@@ -117,3 +117,74 @@ def center_mask(h=512, w=512):
     m = np.zeros((h, w), np.uint8)
     m[h // 4: 3 * h // 4, w // 4: 3 * w // 4] = 255
     return m
+
+
+def make_bpe_vocab(path, n_merges=49152 - 256 - 2, seed=123462):
+    """Synthetic stand-in for `bpe_simple_vocab_16e6.txt.gz` (a download in the reference, clip_tokenizer.py:79-82):
+    a header line and `n_merges` seeded, well-formed merge rules over the CLIP byte alphabet, so that the vocabulary
+    has the published size (49408 ids, <|startoftext|> = 49406, <|endoftext|> = 49407).  The first rules join
+    lower-case letters, so ordinary prompts really exercise multi-level merges."""
+    import gzip
+    from .bpe import byte_symbols
+    rng = np.random.default_rng(seed)
+    sym = list(byte_symbols())
+    letters = [c for c in "abcdefghijklmnopqrstuvwxyz"]
+    inner = list(letters)                      # tokens that can start a merge (no end-of-word mark)
+    final = [c + "</w>" for c in letters]      # tokens carrying the end-of-word mark
+    seen = set(sym) | {s + "</w>" for s in sym}
+    rules = []
+    draws = iter(())
+    while len(rules) < n_merges:
+        nxt = next(draws, None)
+        if nxt is None:  # drawn in bulk: one generator call per rule would dominate the run time
+            draws = iter(rng.random((65536, 4)).tolist())
+            continue
+        r0, r1, r2, r3 = nxt
+        if len(rules) > 30000 and r0 < 0.2:  # some rules over the rest of the alphabet (digits, punctuation)
+            a = sym[int(r1 * 256)]
+        else:
+            a = inner[int(r1 * len(inner))]
+        pool = final if r2 < 0.35 else inner
+        b = pool[int(r3 * len(pool))]
+        tok = a + b
+        if tok in seen or len(tok) > 14:
+            continue
+        seen.add(tok)
+        rules.append(f"{a} {b}")
+        (final if tok.endswith("</w>") else inner).append(tok)
+    with gzip.open(path, "wb") as f:
+        f.write(("#version: synthetic\n" + "\n".join(rules) + "\n").encode("utf-8"))
+    return path
+
+
+def make_lora_state_dict(rank=4, alpha=2.0, every=7, seed=123463) -> dict:
+    """Synthetic kohya-format LoRA (`<module>.alpha`, `.lora_down.weight`, `.lora_up.weight`) over every `every`-th
+    adaptable UNet module — linears, 1x1 and 3x3 convolutions, time projections, shortcuts, resamplers — and the
+    attention / MLP linears of some text-encoder layers.  Module names are the flattened diffusers names LoRA files
+    carry (ckpt_loader.py:2231-2272)."""
+    sd = {}
+    shapes, alias = K.unet_keys(), K.unet_alias_map()
+    skip = ("time_embedding.", "conv_in.", "conv_out.")
+    mods = [(a[:-len(".weight")], shapes[k]) for k, a in alias.items()
+            if a.endswith(".weight") and len(shapes[k]) >= 2 and not a.startswith(skip)]
+    picked = mods[::every] + [m for m in mods if "samplers" in m[0] or "conv_shortcut" in m[0]][:4]
+    for name, shp in picked:
+        flat = "lora_unet_" + name.replace(".", "_")
+        out_c, in_c = shp[0], shp[1]
+        if len(shp) == 4 and shp[2] == 3:
+            down, up = (rank, in_c, 3, 3), (out_c, rank, 1, 1)
+        elif len(shp) == 4:
+            down, up = (rank, in_c, 1, 1), (out_c, rank, 1, 1)
+        else:
+            down, up = (rank, in_c), (out_c, rank)
+        sd[flat + ".lora_down.weight"] = _tensor(flat + ".down", down, seed)
+        sd[flat + ".lora_up.weight"] = _tensor(flat + ".up", up, seed) * 0.5
+        sd[flat + ".alpha"] = torch.tensor(alpha)
+    for layer in (0, 5, 11):
+        for leaf, (o, i) in {"mlp_fc1": (3072, 768), "mlp_fc2": (768, 3072), "self_attn_q_proj": (768, 768),
+                             "self_attn_out_proj": (768, 768)}.items():
+            flat = f"lora_te_text_model_encoder_layers_{layer}_{leaf}"
+            sd[flat + ".lora_down.weight"] = _tensor(flat + ".down", (rank, i), seed)
+            sd[flat + ".lora_up.weight"] = _tensor(flat + ".up", (o, rank), seed) * 0.5
+            sd[flat + ".alpha"] = torch.tensor(alpha)
+    return sd

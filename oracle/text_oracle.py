@@ -49,19 +49,30 @@ def encoder_layer(sd, p, x):
     return x + _linear(sd, p + ".mlp.fc2", h)
 
 
-def text_encode(sd, tokens, clip_skip=-1):
-    """tokens (B,T) int -> context (B,T,768) float32.  TextClipEmbedding (:22-33: token + position embedding, positions
-    0..T-1 as StableDiffusionBase._get_pos_ids gives them), then layers 0 .. 12+clip_skip and the final LayerNorm of
-    out[clip_skip] (:128-133)."""
+def text_embed(sd, tokens, positions=None):
+    """TextClipEmbedding (text_encoder.py:22-33,106-122): token + position embedding -> (B,T,768)."""
     tokens = torch.as_tensor(np.asarray(tokens), dtype=torch.long)
     if tokens.ndim == 1:
         tokens = tokens[None]
     T = tokens.shape[1]
+    pos = torch.arange(T)[None] if positions is None else torch.as_tensor(np.asarray(positions), dtype=torch.long)
+    x = sd["text_model.embeddings.token_embedding.weight"].float()[tokens] + \
+        sd["text_model.embeddings.position_embedding.weight"].float()[pos]
+    return x.numpy().astype(np.float32)
+
+
+def encode_embedded(sd, embedding, clip_skip=-1):
+    """TextEncoder (text_encoder.py:125-135) on a (B,T,768) embedding: layers 0 .. 12+clip_skip, then the final
+    LayerNorm of out[clip_skip] (:128-133)."""
     with torch.no_grad():
-        x = sd["text_model.embeddings.token_embedding.weight"].float()[tokens] + \
-            sd["text_model.embeddings.position_embedding.weight"].float()[:T][None]
+        x = torch.as_tensor(np.asarray(embedding), dtype=torch.float32)
         for i in range(NUM_LAYERS + clip_skip + 1):
             x = encoder_layer(sd, f"text_model.encoder.layers.{i}", x)
         x = F.layer_norm(x, (DIM,), sd["text_model.final_layer_norm.weight"].float(), sd["text_model.final_layer_norm.bias"].float(),
                          eps=1e-5)
     return x.numpy().astype(np.float32)
+
+
+def text_encode(sd, tokens, clip_skip=-1):
+    """tokens (B,T) int -> context (B,T,768) float32: TextEncoder(TextClipEmbedding([tokens, 0..T-1]))."""
+    return encode_embedded(sd, text_embed(sd, tokens), clip_skip)

@@ -171,8 +171,12 @@ def test_generate_image_argument_errors_match_reference():
     from minsdtf_b200.stable_diffusion import StableDiffusionBase
     with pytest.raises(ValueError):  # stable_diffusion.py:377-382
         StableDiffusionBase.generate_image(sd, np.zeros((77, 768), np.float32), diffusion_noise=np.zeros((64, 64, 4)), seed=1)
-    with pytest.raises(NotImplementedError):
-        sd.encode_text("a prompt")  # text tower is outside this round's scope and says so
+    with pytest.raises(FileNotFoundError):
+        sd.encode_text("a prompt")  # string prompts need the CLIP BPE vocabulary, a download in the reference: says so
+    with pytest.raises(ValueError):  # stable_diffusion.py:205-206
+        type(sd).tokenizer.fset(sd, object()) or sd.encode_text("a prompt", "/no/such/embedding.pt")
+    with pytest.raises(ValueError):  # both GPUs of a CFG pair must start from the same latent
+        StableDiffusionBase.generate_image(sd, np.zeros((77, 768), np.float32), cfg_split=True)
 
 
 # ------------------------------------------------------------------------------------------------ oracle graphs

@@ -73,9 +73,14 @@ def _check_attention(engine, B, Nq, Nk, heads, d, legacy):
     vh = v.view(B, Nk, heads, d).permute(0, 2, 1, 3).cuda()
     s = torch.matmul(qh, kh.transpose(-1, -2)) * d ** -0.5
     ref = torch.matmul(torch.softmax(s, -1), vh).permute(0, 2, 1, 3).reshape(B, Nq, C).cpu().numpy()
-    err = np.abs(out - ref).max()
     assert np.isfinite(out).all()
-    assert err < 2e-2, f"max abs err {err} (ref max {np.abs(ref).max()})"
+    # relative bars (the output of a long softmax average is small: absmax 0.13 at 4096 keys, 0.08 at 9216):
+    # max|d| / max|ref| <= 2e-2 (the eps bar of BASELINE.json) and rms(d) / rms(ref) <= 1e-2
+    d = out.astype(np.float64) - ref
+    rel_max = np.abs(d).max() / np.abs(ref).max()
+    rel_rms = np.sqrt(np.mean(d * d)) / np.sqrt(np.mean(ref.astype(np.float64) ** 2))
+    assert rel_max <= 2e-2, f"max|d|/max|ref| = {rel_max:.4g} (max|ref| {np.abs(ref).max():.4g})"
+    assert rel_rms <= 1e-2, f"rms(d)/rms(ref) = {rel_rms:.4g}"
 
 
 @pytest.mark.parametrize("B,H,W,C,mode", [

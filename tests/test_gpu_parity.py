@@ -31,7 +31,8 @@ def temb(t, B):
     return np.repeat(timestep_embedding(t)[None], B, axis=0)
 
 
-@pytest.mark.parametrize("B,h,T,t", [(1, 16, 77, 500), (2, 32, 77, 960), (1, 64, 77, 20), (2, 64, 77, 480), (1, 32, 154, 700)])
+@pytest.mark.parametrize("B,h,T,t", [(1, 16, 77, 500), (2, 32, 77, 960), (1, 64, 77, 20), (2, 64, 77, 480), (1, 32, 154, 700),
+                                     (1, 96, 77, 500)])  # 96 = the 768x768 configuration (9216-token self-attention)
 def test_unet_eps_parity(engine_unet, unet_sd, B, h, T, t):
     lat = synth.latents(B, h, h, seed=11 + h)
     ctx = synth.context(B, T, seed=12 + T)
@@ -241,3 +242,123 @@ def test_img2img_inpaint_controlnet_tcd_paths(engine_unet, engine_vae, engine_cn
                                  return_latent=True)
     print(f"tcd final latent rel err {rel(got, ref):.4g}")
     assert rel(got, ref) <= 5e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# BASELINE.json configurations at FULL size against the oracle (VERDICT r01 "what's weak" 2): every model at the
+# tensor shapes the benchmark runs, so the 64-CTA GroupNorm partitions, the 512x512x128/256 decoder tensors and the
+# 4096 / 9216-token attention meet the oracle too.  The oracle side costs tens of seconds of CPU per test.
+# ----------------------------------------------------------------------------------------------------------------
+def test_vae_decode_full_size_512(engine_vae, vae_sd):
+    """config 1/2 decode: 64x64 latent -> 512x512 image, >= 30 dB against the oracle from the identical latent"""
+    lat = synth.latents(1, 64, 64, seed=131) * 0.18215 * 3.0
+    ref = O.vae_decode(vae_sd, lat)
+    got = engine_vae.vae_decode(lat)
+    assert got.shape == (1, 512, 512, 3) and np.isfinite(got).all()
+    p = psnr_u8(engine_vae.to_uint8(got), O.to_uint8(ref))
+    print(f"vae decode 512x512: rel {rel(got, ref):.4g} psnr {p:.2f} dB")
+    assert p >= 30.0, p
+
+
+def test_vae_encode_full_size_512(engine_vae, vae_sd):
+    """config 3 encode: 512x512 image -> 64x64 latent"""
+    img = synth.smooth_image(512, 512).astype(np.float32)[None] / 127.5 - 1.0
+    ref = O.vae_encode(vae_sd, img)
+    got = engine_vae.vae_encode(img)
+    assert got.shape == (1, 64, 64, 4)
+    print(f"vae encode 512x512: rel {rel(got, ref):.4g}")
+    assert rel(got, ref) <= EPS_BAR, rel(got, ref)
+
+
+def test_controlnet_and_hintnet_full_size_64(engine_unet, engine_cnet, unet_sd, cnet_sd):
+    """config 4: HintNet on a 512x512 edge map, ControlNet at the 64x64 latent, residual injection into the UNet"""
+    B, h = 1, 64
+    img = (synth.edge_map(8 * h, 8 * h).astype(np.float32) / 255.0)[None]
+    hint_ref = O.hintnet_forward(cnet_sd, img)
+    hint = engine_cnet.hintnet(img)
+    assert rel(hint, hint_ref) <= EPS_BAR, rel(hint, hint_ref)
+    lat, ctx, te = synth.latents(B, h, h, seed=121), synth.context(B, 77, seed=122), temb(440, B)
+    ctr_ref = O.controlnet_forward(cnet_sd, lat, te, ctx, hint_ref)
+    ctr = engine_cnet.controlnet(lat, te, ctx, hint_ref)
+    worst = max(rel(a, b) for a, b in zip(ctr, ctr_ref))
+    print(f"controlnet 64x64: hint rel {rel(hint, hint_ref):.4g}, worst residual rel {worst:.4g}")
+    assert worst <= EPS_BAR, worst
+    ref = O.unet_forward(unet_sd, lat, te, ctx, ctr_ref)
+    got = engine_unet.unet(lat, te, ctx, ctr_ref)
+    assert rel(got, ref) <= EPS_BAR, rel(got, ref)
+
+
+def test_config1_full_size_25_steps_against_oracle(engine_unet, engine_vae, unet_sd, vae_sd):
+    """BASELINE config 1 as written: 512x512, batch 1, 25 DDIM steps, CFG 7.5 (rescale 0.7, the API default), the same
+    seeded start latent on both sides.  Free-running: the engine's own loop (one captured graph) against the oracle's
+    50 UNet calls; plus teacher-forced eps parity at the first, a middle and the last step of the oracle trajectory."""
+    B, h, steps = 1, 64, 25
+    noise, ctx, unc = synth.latents(B, h, h), synth.context(B), synth.uncond_context(B)
+    trace = {}
+    img_ref = O.generate_image({"unet": unet_sd, "vae": vae_sd}, ctx, unc, noise, num_steps=steps, guidance_scale=7.5,
+                               guidance_rescale=0.7, trace=trace)
+    assert trace["t"][0] == 960 and trace["t"][-1] == 0 and len(trace["t"]) == steps
+    for i in (0, 12, 24):
+        lat, t = trace["latent_in"][i], trace["t"][i]
+        ec = engine_unet.unet(lat, temb(t, B), ctx)
+        assert rel(ec, trace["eps_c"][i]) <= EPS_BAR, (i, t, rel(ec, trace["eps_c"][i]))
+    sd = _pipeline(engine_unet, img_height=8 * h, img_width=8 * h)
+    sd.unconditional_context = unc[:1]
+    img, lat = sd.generate_image(ctx, batch_size=B, num_steps=steps, diffusion_noise=noise, guidance_rescale=0.7,
+                                 return_latent=True)
+    lat_ref = trace["latent_out"][-1]
+    r, p = rel(lat, lat_ref), psnr_u8(img, img_ref)
+    print(f"config 1 (64x64 latent, 25 steps) free-running: final latent rel err {r:.4g}, image psnr {p:.2f} dB")
+    assert img.shape == (B, 512, 512, 3) and img.dtype == np.uint8
+    assert r <= 0.1, r
+    assert p >= 25.0, p
+    dec = engine_vae.to_uint8(engine_vae.vae_decode(np.asarray(lat_ref, np.float32)))
+    p_tf = psnr_u8(dec, img_ref)
+    print(f"config 1 decode from the oracle's final latent: {p_tf:.2f} dB")
+    assert p_tf >= 30.0, p_tf
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the three public entry points themselves (stable_diffusion.py:84-174), token-id prompts through the engine's text tower
+# ----------------------------------------------------------------------------------------------------------------
+def test_public_entry_points_text_to_image_image_to_image_inpaint(engine_unet, engine_vae, unet_sd, vae_sd):
+    from oracle import text_oracle as TO
+    B, h, H = 1, 16, 128
+    text_sd = synth.make_state_dict("text_encoder")
+    if "text_encoder" not in engine_unet.loaded:
+        engine_unet.load_state_dict(text_sd, "text_encoder")
+    sd = _pipeline(engine_unet, img_height=H, img_width=H)
+    tokens, neg = synth.prompt_tokens(1, seed=5)[0], synth.prompt_tokens(1, seed=6)[0]
+    ctx_ref, unc_ref = TO.text_encode(text_sd, tokens[None], -1), TO.text_encode(text_sd, neg[None], -1)
+    noise = synth.latents(B, h, h, seed=41)
+    weights = {"unet": unet_sd, "vae": vae_sd}
+    seen = []
+    # text_to_image: defaults guidance 7.5, rescale 0.7 (:84-96); diffusion_noise is not a kwarg there, so seed= it is
+    sd._get_initial_diffusion_noise = lambda batch_size, seed: noise  # the reference draws TF Philox noise here
+    img = sd.text_to_image(tokens, negative_prompt=neg, batch_size=B, num_steps=4, seed=7, callback=seen.append)
+    ref = O.generate_image(weights, ctx_ref, unc_ref, noise, num_steps=4, guidance_scale=7.5, guidance_rescale=0.7)
+    p = psnr_u8(img, ref)
+    print(f"text_to_image psnr {p:.2f} dB, callback saw {seen}")
+    assert img.shape == (B, H, H, 3) and p >= 28.0, p
+    assert seen == [1, 2, 3, 4]  # once per iteration, as stable_diffusion.py:476-478
+    # image_to_image: 10 steps x 0.8
+    src, msk = synth.smooth_image(H, H), synth.center_mask(H, H)
+    in_arr, in_t = sd.preprocessed_image(src)
+    init_ref = O.vae_encode(vae_sd, in_t)
+    img = sd.image_to_image(tokens, negative_prompt=neg, batch_size=B, num_steps=10, seed=7, reference_image=src,
+                            reference_image_strength=0.8)
+    ref = O.generate_image(weights, ctx_ref, unc_ref, noise, num_steps=10, guidance_scale=7.5, guidance_rescale=0.7,
+                           init_latent=init_ref, strength=0.8)
+    p = psnr_u8(img, ref)
+    print(f"image_to_image psnr {p:.2f} dB")
+    assert p >= 28.0, p
+    # inpaint
+    m_arr, m_lat = sd.preprocessed_mask(msk, 5)
+    img = sd.inpaint(tokens, negative_prompt=neg, batch_size=B, num_steps=10, seed=7, reference_image=src,
+                     reference_image_strength=0.8, inpaint_mask=msk, mask_blur_strength=5)
+    ref = O.generate_image(weights, ctx_ref, unc_ref, noise, num_steps=10, guidance_scale=7.5, guidance_rescale=0.7,
+                           init_latent=init_ref, strength=0.8, latent_mask=m_lat, input_image_array=in_arr,
+                           input_mask_array=m_arr)
+    p = psnr_u8(img, ref)
+    print(f"inpaint psnr {p:.2f} dB")
+    assert p >= 28.0, p
