@@ -9,8 +9,14 @@ One "step" = one full generation of the per-GPU batch: 25 denoising steps (50 UN
 `value`  : images/s with every input already resident in HBM (torch CUDA tensors borrowed through DLPack), device time.
 `e2e`    : images/s through the public API `StableDiffusion.generate_image` with HOST (NumPy) buffers — H2D of
            latents/contexts and D2H of the uint8 images are inside the timed region.
-`roofline`: the dominant kernel (tcgen05 implicit-GEMM conv, 3x3 320->320 @64x64 x effective batch 16) timed live with
-           CUDA events on the engine's stream, against the measured cuBLAS bf16 peak of MEASURED_PEAKS.json.
+`roofline`: the dominant kernel AS THE STEP USES IT — the tcgen05 implicit-GEMM kernel (conv_gemm3_kernel: every conv and
+           linear) over ALL its launches of one denoise step: summed algorithmic FLOP / summed CUDA-event time of those
+           launches (sdtf_trace_begin/end: eager launches on the engine's stream, each bracketed by events), against the
+           measured cuBLAS bf16 peak of MEASURED_PEAKS.json (burst; `frac_sustained` against the back-to-back figure).
+           `roofline_best_shape` keeps the isolated 3x3 320->320 @64x64 number; `operator_classes` lists conv / attention /
+           GroupNorm / LayerNorm totals per denoise step and for the VAE decode (GB/s of algorithmic bytes for the norms).
+`strong_scaling` (N > 1): BASELINE configs[1] read literally — 8 prompts TOTAL, 8/N per GPU — measured in the same run;
+           `--scaling strong` makes that the headline value instead of the weak one.
 `cpu_baseline`: the oracle (torch-fp32 restatement of the reference graphs; Keras/TensorFlow are not installable
            offline) timed on this box's host cores on a bounded sample of the same workload.
 """
@@ -46,6 +52,9 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="run the resident step --steps times and exit (for ncu)")
     ap.add_argument("--no-cfg-split", action="store_true", help="skip the extra CFG-split (GPU pairs + NCCL) measurement at N >= 2")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --batch prompts per GPU (default); strong: --batch prompts in total, batch/N per GPU")
+    ap.add_argument("--no-strong", action="store_true", help="skip the extra strong-scaling measurement at N >= 2")
     return ap.parse_args()
 
 
@@ -90,6 +99,13 @@ def ncu_traffic(kernel_label):
         return int(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel_label]["traffic"])
     except Exception:
         return None
+
+
+def measured_hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6400.0, "fallback (B200_PROFILING.md)"
 
 
 def measured_peak():
@@ -193,6 +209,10 @@ def run_engine(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     B, S, size = args.batch, args.denoise_steps, args.size
+    if args.scaling == "strong":
+        if args.batch % world:
+            raise SystemExit(f"--scaling strong: {args.batch} prompts do not divide over {world} GPUs")
+        B = args.batch // world
     h = size // 8
     sd = StableDiffusion(img_height=size, img_width=size, synthetic=True, device=local_rank)
     sd.load_all()
@@ -285,6 +305,37 @@ def run_engine(args, rank, world, local_rank):
                       "pairs": world // 2, "prompts_per_pair": Bp, "exchange": "ncclAllGather of eps (B,64,64,4) f32 per step, in-graph",
                       "timing": "host wall clock around K generations incl. barrier (max over ranks)"}
         assert tuple(imgs.shape) == (B, size, size, 3)
+        # self-check: the split loop must reproduce the single-GPU batched loop on the same inputs (4 steps, eager and graph)
+        worst = 0.0
+        for graph in (False, True):
+            a = eng.denoise(p_noise[:2], p_ctx[:2], p_unc[:2], d_temb[:4], coefs[:4], decode=False, use_cuda_graph=graph, cfg_split=True)
+            b = eng.denoise(p_noise[:2], p_ctx[:2], p_unc[:2], d_temb[:4], coefs[:4], decode=False, use_cuda_graph=graph, cfg_split=False)
+            worst = max(worst, float((a - b).abs().max()))
+        wt = torch.tensor([worst], dtype=torch.float64, device=dev)
+        dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+        split_info["max_abs_diff_vs_unsplit_loop"] = wt.item()
+        split_info["equals_unsplit_loop"] = bool(wt.item() <= 1e-5)
+        assert split_info["equals_unsplit_loop"], f"CFG split differs from the single-GPU loop by {wt.item()}"
+        eng.comm_destroy()
+
+    # ---- strong scaling (BASELINE configs[1] read literally: `--batch` prompts in TOTAL, batch/N per GPU) ----
+    strong_info = None
+    if world >= 2 and args.scaling == "weak" and not args.no_strong and args.batch % world == 0:
+        Bs = args.batch // world
+        s_noise, s_ctx, s_unc = d_noise[:Bs].contiguous(), d_ctx[:Bs].contiguous(), d_unc[:Bs].contiguous()
+        for _ in range(max(1, min(args.warmup, 3))):
+            eng.denoise(s_noise, s_ctx, s_unc, d_temb, coefs, decode=True, use_cuda_graph=use_graph)
+        barrier()
+        s_ms = 0.0
+        for _ in range(args.steps):
+            eng.denoise(s_noise, s_ctx, s_unc, d_temb, coefs, decode=True, use_cuda_graph=use_graph)
+            s_ms += eng.timings()["total_ms"]
+        barrier()
+        st = torch.tensor([s_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+        strong_info = {"value": args.batch * args.steps / (st.item() / 1e3), "unit": "images/s", "scaling": "strong",
+                       "prompts_total": args.batch, "prompts_per_gpu": Bs, "unet_batch_per_gpu": 2 * Bs,
+                       "ms_per_step": st.item() / args.steps, "timing": "device time of the whole call (CUDA events), max over ranks"}
 
     # ---- max over ranks ----
     t = torch.tensor([dev_ms, wall, wall_e2e, loop_ms, dec_ms], dtype=torch.float64, device=dev)
@@ -300,33 +351,77 @@ def run_engine(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
 
     if rank == 0:
-        # dominant kernel, timed alone with CUDA events on the engine's stream (rotating > L2 worth of operands)
+        # ---- operator classes of ONE denoise step and of the VAE decode: eager launches, CUDA events around every operator ----
+        eng.trace_begin()
+        eng.denoise(d_noise, d_ctx, d_unc, d_temb[:2], coefs[:2], decode=False, use_cuda_graph=False)
+        tr_unet = eng.trace_end()
+        eng.trace_begin()
+        eng.vae_decode(d_noise * 0.18215)
+        tr_dec = eng.trace_end()
+        hbm_peak, hbm_src = measured_hbm_peak()
+        sustained = measured_sustained_peak()
+
+        def classes(tr, div):
+            out, tot = {}, sum(v["us"] for v in tr.values())
+            for k, v in tr.items():
+                if not v["launches"]:
+                    continue
+                e = {"launches": v["launches"] // div, "ms": v["us"] / div / 1e3, "share_of_operator_time": v["us"] / tot}
+                if k in ("conv", "attn"):
+                    e["tflops"] = v["flop"] / v["us"] / 1e6
+                    e["frac_of_burst_peak"] = e["tflops"] / peak
+                else:
+                    e["gbs"] = v["bytes"] / v["us"] / 1e3
+                    e["frac_of_hbm_peak"] = e["gbs"] / hbm_peak
+                out[k] = e
+            return out
+
+        cls_unet, cls_dec = classes(tr_unet, 2), classes(tr_dec, 1)
+        conv = tr_unet["conv"]
+        conv_step_tflops = conv["flop"] / conv["us"] / 1e6
+        # the isolated best shape (what round 1 reported as `roofline`), kept for continuity
         conv_ms = eng.bench_conv(2 * B, 64, 320, 320, 3, reps=40)
         conv_tflops = CONV_GFLOP * 2 * B / conv_ms
         conv_label = "conv_gemm3_kernel 3x3 320->320 @64x64, batch %d" % (2 * B)
+        par = f"dp{world} over prompts, no per-step collective"
+        if args.scaling == "strong":
+            par += f"; strong scaling: {args.batch} prompts in total, {B} per GPU"
         line = {
             "metric": "images_per_second", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": f"SD1.5 text_to_image {size}x{size}, {B} prompts per GPU, {S} DDIM steps, CFG 7.5 "
                                    f"(cond+uncond batched: UNet batch {2 * B}), guidance_rescale 0.7, random-init weights, "
                                    f"synthetic contexts (BASELINE.json configs[1])",
-                       "parallelism": f"dp{world} over prompts, no per-step collective",
+                       "parallelism": par,
                        "l2": "per-iteration working set (1.7 GB bf16 weights + GBs of activations) >> 126 MB L2; no flush needed",
                        "cuda_graph": use_graph},
-            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(noise.nbytes + ctx.nbytes + unc.nbytes + t_emb.nbytes),
+            "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": int(noise[:B].nbytes + ctx[:B].nbytes + unc[:B].nbytes + t_emb.nbytes),
                     "d2h_bytes_per_step": int(B * size * size * 3), "ms_per_step": wall_e2e / K * 1e3},
             "gpu_launches": int(launches),
             "unet_step_ms": unet_step_ms, "unet_step_tflops": unet_tflops, "unet_step_frac_of_peak": unet_tflops / peak,
-            "unet_step_frac_of_sustained_peak": (unet_tflops / measured_sustained_peak()) if measured_sustained_peak() else None,
+            "unet_step_frac_of_sustained_peak": (unet_tflops / sustained) if sustained else None,
             "decode_ms_per_batch": dec_ms / K, "wall_ms_per_step": wall / K * 1e3,
-            "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
-                         "traffic": ncu_traffic(conv_label), "kernel": conv_label,
-                         "flop_per_launch": CONV_GFLOP * 2 * B * 1e9, "ms_per_launch": conv_ms, "peak_source": peak_src},
+            "roofline": {"bound": "tensor", "achieved": conv_step_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_step_tflops / peak,
+                         "frac_sustained": (conv_step_tflops / sustained) if sustained else None,
+                         "traffic": ncu_traffic("conv_gemm3_kernel step average"),
+                         "kernel": "conv_gemm3_kernel: all %d conv / linear launches of one denoise step (UNet batch %d), FLOP-weighted"
+                                   % (conv["launches"] // 2, 2 * B),
+                         "flop_per_launch": conv["flop"] / conv["launches"], "ms_per_launch": conv["us"] / conv["launches"] / 1e3,
+                         "ms_per_step_in_kernel": conv["us"] / 2 / 1e3,
+                         "share_of_operator_time": conv["us"] / sum(v["us"] for v in tr_unet.values()),
+                         "how": "sdtf_trace_begin/end: eager launches on the engine's stream, CUDA events around every operator",
+                         "peak_source": peak_src},
+            "roofline_best_shape": {"bound": "tensor", "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
+                                    "traffic": ncu_traffic(conv_label), "kernel": conv_label,
+                                    "flop_per_launch": CONV_GFLOP * 2 * B * 1e9, "ms_per_launch": conv_ms},
+            "operator_classes": {"denoise_step": cls_unet, "vae_decode": cls_dec, "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src},
             "clocks": clocks,
         }
         if split_info is not None:
             line["cfg_split"] = split_info
+        if strong_info is not None:
+            line["strong_scaling"] = strong_info
         if not args.skip_cpu_baseline and world == 1:
             v, cores, sample, _, _ = cpu_reference_rate(S, size)
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}

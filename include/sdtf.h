@@ -177,6 +177,17 @@ int sdtf_comm_unique_id(const char* nccl_lib, void* out_id128);
 int sdtf_comm_init(sdtf_engine* e, const char* nccl_lib, const void* id128, int32_t rank, int32_t world);
 int sdtf_comm_destroy(sdtf_engine* e);
 
+/* Operator-class accounting for bench.py's roofline line: between sdtf_trace_begin and sdtf_trace_end every conv /
+ * linear, attention, GroupNorm and LayerNorm launch is issued eagerly (no CUDA graph) and bracketed by CUDA events on
+ * the engine's stream; sdtf_trace_end returns, per class, the launch count, the summed device time and the summed
+ * ALGORITHMIC work (FLOP = 2 MAC of the contraction; bytes = minimal reads + writes) of those launches. */
+typedef struct {
+  int64_t launches[4];  /* conv/linear GEMM, attention, GroupNorm, LayerNorm */
+  double us[4], flop[4], bytes[4];
+} sdtf_trace_summary;
+int sdtf_trace_begin(sdtf_engine* e);
+int sdtf_trace_end(sdtf_engine* e, sdtf_trace_summary* out);
+
 /* kernel micro-benchmarks used by bench.py for the roofline line: runs `reps` launches of one representative
  * contraction of the UNet (3x3 conv, batch*hw x cin -> cout) on device-resident synthetic data and returns the
  * average CUDA-event time per launch in ms. */

@@ -19,7 +19,7 @@ EXPORTS = [
     "sdtf_unet_forward", "sdtf_controlnet_forward", "sdtf_hintnet_forward", "sdtf_vae_decode", "sdtf_vae_encode", "sdtf_text_encode",
     "sdtf_text_embed", "sdtf_text_encode_embedded",
     "sdtf_cfg_sched_step", "sdtf_to_uint8", "sdtf_denoise", "sdtf_get_timings", "sdtf_bench_conv", "sdtf_bench_attention",
-    "sdtf_test_attention", "sdtf_test_norm", "sdtf_comm_unique_id", "sdtf_comm_init", "sdtf_comm_destroy",
+    "sdtf_test_attention", "sdtf_test_norm", "sdtf_trace_begin", "sdtf_trace_end", "sdtf_comm_unique_id", "sdtf_comm_init", "sdtf_comm_destroy",
 ]
 
 
@@ -45,6 +45,11 @@ ON_STEP = ctypes.CFUNCTYPE(None, ctypes.c_int32, ctypes.c_void_p)  # void (*on_s
 class Timings(ctypes.Structure):
     _fields_ = [("loop_ms", ctypes.c_float), ("decode_ms", ctypes.c_float), ("total_ms", ctypes.c_float),
                 ("kernel_launches", ctypes.c_int32)]
+
+
+class TraceSummary(ctypes.Structure):
+    _fields_ = [("launches", ctypes.c_int64 * 4), ("us", ctypes.c_double * 4), ("flop", ctypes.c_double * 4),
+                ("bytes", ctypes.c_double * 4)]
 
 
 _lib = None
@@ -88,6 +93,8 @@ def load():
     lib.sdtf_comm_unique_id.argtypes = [ctypes.c_char_p, vp]
     lib.sdtf_comm_init.argtypes = [vp, ctypes.c_char_p, vp, i32, i32]
     lib.sdtf_comm_destroy.argtypes = [vp]
+    lib.sdtf_trace_begin.argtypes = [vp]
+    lib.sdtf_trace_end.argtypes = [vp, ctypes.POINTER(TraceSummary)]
     lib.sdtf_test_attention.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.sdtf_test_norm.argtypes = [vp, vp, vp, vp, i32, vp]
     for name in EXPORTS:

@@ -270,6 +270,44 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// Packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two lanes' worth of FMA work).  The softmax warps of the
+// d = 40 kernel are bound by instruction issue and by the 16-lane MUFU together (ncu r01: issue 64 %, xu 52 %), so the
+// scale-and-subtract of every score and the polynomial 2^x run as pairs.
+using f32x2 = unsigned long long;
+__device__ __forceinline__ f32x2 pack2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for a pair on the FMA / ALU pipes (same Cody-Waite split + cubic as ex2_poly); inputs are clamped to >= -126
+__device__ __forceinline__ void ex2_poly2(f32x2 x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x2 = pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const f32x2 magic = pack2(12582912.f, 12582912.f), nmagic = pack2(-12582912.f, -12582912.f);
+  const f32x2 t = add2(x2, magic);                       // low mantissa bits of t hold n = round(x)
+  const f32x2 f = fma2(add2(t, nmagic), pack2(-1.f, -1.f), x2);  // x - n in [-0.5, 0.5]
+  f32x2 p = fma2(pack2(0.0555041f, 0.0555041f), f, pack2(0.2402265f, 0.2402265f));
+  p = fma2(p, f, pack2(0.6931472f, 0.6931472f));
+  p = fma2(p, f, pack2(1.0f, 1.0f));
+  float p0, p1, t0, t1;
+  unpack2(p, p0, p1);
+  unpack2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 static constexpr int kA2Threads = 352;
 #define A2_TIMED(acc, stmt)                    \
   do {                                         \
@@ -588,7 +626,9 @@ __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 2, 5
 
 // DEFER (A/B switch SDTF_ATTN_DEFER = 0 | 16 | 32): exponentials of the first DEFER keys of a tile are computed into
 // registers BEFORE waiting for P V_{j-1} (the wait only guards the P buffer and the rare O rescale).
-template <int KS, int DV, int DEFER>
+// PP16: score pairs out of every 8 (16 keys) whose exponentials run on the FMA pipe instead of MUFU.EX2 (2 = a quarter,
+// 3 = three eighths, 4 = half); 0 selects the round-1 scalar code (2 of 8 scalar polynomials) for A/B runs.
+template <int KS, int DV, int DEFER, int PP16>
 __global__ void __launch_bounds__(kAHThreads, 1)
 attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -800,12 +840,30 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;  // no valid key yet: every term below becomes 2^-inf = 0
       // (masked keys were set to -inf above: 2^-inf = 0 on the MUFU path, 2^-126 on the FMA path — below anything bf16 keeps)
+      const f32x2 scale2 = pack2(p.scale_log2, p.scale_log2), negm2 = pack2(neg_m, neg_m);
       auto exp8 = [&](int c) {
         float e[8];
+        if (PP16 == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xarg = fmaf(__uint_as_float(sv[c + i]), p.scale_log2, neg_m);
-          e[i] = (i >= 6) ? ex2_poly(xarg) : ex2f(xarg);  // 2 of 8 on the FMA pipe
+          for (int i = 0; i < 8; ++i) {
+            const float xarg = fmaf(__uint_as_float(sv[c + i]), p.scale_log2, neg_m);
+            e[i] = (i >= 6) ? ex2_poly(xarg) : ex2f(xarg);  // 2 of 8 on the FMA pipe
+          }
+        } else {
+          // pairs on the FMA pipe in this block of 8 keys: PP16 / 2, the odd one going to the odd blocks
+          const int npoly = (PP16 >> 1) + ((PP16 & 1) & (c >> 3));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const f32x2 x2 = fma2(pack2(__uint_as_float(sv[c + 2 * j]), __uint_as_float(sv[c + 2 * j + 1])), scale2, negm2);
+            if (j >= 4 - npoly) {
+              ex2_poly2(x2, e[2 * j], e[2 * j + 1]);
+            } else {
+              float x0, x1;
+              unpack2(x2, x0, x1);
+              e[2 * j] = ex2f(x0);
+              e[2 * j + 1] = ex2f(x1);
+            }
+          }
         }
         uint4 w;
         w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]);
@@ -1155,9 +1213,11 @@ inline void init_attn_kernels() {
   static_assert(attn2q_smem_bytes<2, 2, 1>() <= 232448, "d = 80 two-tile attention must fit 227 KB of shared memory");
   SDTF_CUDA(cudaFuncSetAttribute(attn2q_kernel<2, 5, 80, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)attn2q_smem_bytes<2, 2, 1>()));
-  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
-  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
-  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
   init_attn_t<2, 5, 80, 2, 2>();
   init_attn_t<3, 10, 160, 1, 1>();
   static_assert(xattn_smem_bytes<2, 3>() <= 232448, "d = 80 cross-attention must fit 227 KB of shared memory");
@@ -1220,10 +1280,16 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
       static const int use_2q = getenv("SDTF_ATTN_2Q") ? atoi(getenv("SDTF_ATTN_2Q")) : 0;  // A/B: previous full-row kernel
       if (!use_2q) {
         SDTF_CHECK(a.d < 48, "attn2h keeps the softmax denominator in accumulator column d: needs d < DV");
-        static const int defer = getenv("SDTF_ATTN_DEFER") ? atoi(getenv("SDTF_ATTN_DEFER")) : 16;  // measured: 0.735 / 0.724 / 0.756 ms for 0 / 16 / 32
-        if (defer == 16) launch_pdl(attn2h_kernel<3, 48, 16>, grid, dim3(kAHThreads), attn2h_smem_bytes(), stream, 1, tq, tk, tv, p);
-        else if (defer == 32) launch_pdl(attn2h_kernel<3, 48, 32>, grid, dim3(kAHThreads), attn2h_smem_bytes(), stream, 1, tq, tk, tv, p);
-        else launch_pdl(attn2h_kernel<3, 48, 0>, grid, dim3(kAHThreads), attn2h_smem_bytes(), stream, 1, tq, tk, tv, p);
+        // SDTF_ATTN_PP16 (A/B): exponential pairs per 16 keys on the FMA pipe — 0: round-1 scalar code, 2 / 3 / 4 packed;
+        // SDTF_ATTN_DEFER (round 1: 0.735 / 0.724 / 0.756 ms for 0 / 16 / 32): 0 or 16
+        static const int defer = getenv("SDTF_ATTN_DEFER") ? atoi(getenv("SDTF_ATTN_DEFER")) : 16;
+        static const int pp16 = getenv("SDTF_ATTN_PP16") ? atoi(getenv("SDTF_ATTN_PP16")) : 3;
+        const size_t sm = attn2h_smem_bytes();
+        if (defer == 0) launch_pdl(attn2h_kernel<3, 48, 0, 3>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
+        else if (pp16 == 0) launch_pdl(attn2h_kernel<3, 48, 16, 0>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
+        else if (pp16 == 2) launch_pdl(attn2h_kernel<3, 48, 16, 2>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
+        else if (pp16 == 4) launch_pdl(attn2h_kernel<3, 48, 16, 4>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
+        else launch_pdl(attn2h_kernel<3, 48, 16, 3>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
         SDTF_CUDA(cudaGetLastError());
         return;
       }

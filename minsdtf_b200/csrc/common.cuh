@@ -109,9 +109,12 @@ inline CUtensorMap make_act_tmap(const View& v, int bw, int bh, int bn, int stri
 // epilogue map over an NHWC output / residual view: dims (C, W, H, B); box (32 channels, bw, bh, bn) = 128 pixels x
 // 64 bytes, 64-byte swizzle (the layout the GEMM epilogue stages its bf16 sub-tiles in).  Stores are clipped and
 // loads zero-filled at the tensor edges by the hardware.
-inline CUtensorMap make_epi_tmap(const bf16* base, int C, int W, int H, int B, long long ld, int bw, int bh, int bn) {
+// `step` > 1: the W x H grid addresses every step-th pixel of a (step W) x (step H) tensor (the parity classes of a
+// folded nearest-upsample convolution write interleaved output pixels; base points at the class's first pixel).
+inline CUtensorMap make_epi_tmap(const bf16* base, int C, int W, int H, int B, long long ld, int bw, int bh, int bn, int step = 1) {
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+  const uint64_t px = (uint64_t)ld * 2 * step, row = (uint64_t)W * step * ld * 2 * step;
+  uint64_t strides[3] = {px, row, (uint64_t)H * step * W * step * ld * 2};
   uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
   uint32_t es[4] = {1, 1, 1, 1};
   return make_tmap_bf16(base, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_64B);

@@ -62,6 +62,10 @@ struct RawTensor {  // a checkpoint tensor staged on the device as fp32, PyTorch
   }
 };
 
+struct UpConvW {  // nearest-2x upsample + 3x3 conv folded into four 2x2 convs (ops.cuh pack_upconv_kernel)
+  PackedWeight cls[4];  // parity class 2 py + px
+};
+
 struct NormW {
   float* gamma = nullptr;
   float* beta = nullptr;
@@ -94,9 +98,20 @@ inline int skip_mask() {
 // SDTF_TRACE=1 (debug, eager launches only): every operator is bracketed by CUDA events on the engine's stream and
 // one line per launch goes to stderr — kind, shape, microseconds, TFLOP/s and GB/s of algorithmic work — in graph order,
 // with the caches in the state the previous operator left them (unlike an ncu replay).  tools/trace_table.py sums it.
+// Per-operator-class totals collected while tracing (sdtf_trace_begin / sdtf_trace_end: bench.py's roofline line is the
+// FLOP-weighted rate of the conv / linear kernel over ALL its launches of one denoise step, not one hand-picked shape).
+struct TraceTotals {
+  long long launches[4] = {0, 0, 0, 0};  // conv, attn, gn, ln
+  double us[4] = {0, 0, 0, 0}, flop[4] = {0, 0, 0, 0}, bytes[4] = {0, 0, 0, 0};
+  bool collecting = false, quiet = false;
+};
+inline TraceTotals& trace_totals() {
+  static TraceTotals t;
+  return t;
+}
 inline int trace_level() {
   static const int v = getenv("SDTF_TRACE") ? atoi(getenv("SDTF_TRACE")) : 0;
-  return v;
+  return (v == 0 && trace_totals().collecting) ? 1 : v;
 }
 inline bool trace_on() { return trace_level() != 0; }
 
@@ -138,8 +153,14 @@ struct Ctx {
     SDTF_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;
     SDTF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-    fprintf(stderr, "[trace] %-6s %-44s %9.2f us %8.1f TFLOP/s %8.1f GB/s\n", kind, shape.c_str(), ms * 1e3, flop / (ms * 1e9),
-            bytes / (ms * 1e6));
+    TraceTotals& tt = trace_totals();
+    if (tt.collecting) {
+      const int k = kind[0] == 'c' ? 0 : kind[0] == 'a' ? 1 : kind[0] == 'g' ? 2 : 3;
+      ++tt.launches[k]; tt.us[k] += ms * 1e3; tt.flop[k] += flop; tt.bytes[k] += bytes;
+    }
+    if (!tt.quiet)
+      fprintf(stderr, "[trace] %-6s %-44s %9.2f us %8.1f TFLOP/s %8.1f GB/s\n", kind, shape.c_str(), ms * 1e3, flop / (ms * 1e9),
+              bytes / (ms * 1e6));
   }
   // fingerprint of the last sample of an NHWC view (SDTF_TRACE=2, eager launches only)
   void fingerprint(const char* kind, const bf16* p, long long ld, int C, long long pixels_per_sample, int B) {
@@ -188,7 +209,7 @@ struct Ctx {
     traced("conv", buf, 2.0 * M * w.N * K * w.kh * w.kw,
            2.0 * ((double)a.a0.B * a.a0.H * a.a0.W * K + M * Nout * (a.res ? 2 : 1) + (double)w.N * K * w.kh * w.kw),
            [&] { launch_conv(st, a); });
-    if (!a.out_fp32) fingerprint("conv", reinterpret_cast<const bf16*>(a.out), a.out_ld, Nout, (long long)a.outH * a.outW, a.a0.B);
+    if (!a.out_fp32 && a.out_step == 1) fingerprint("conv", reinterpret_cast<const bf16*>(a.out), a.out_ld, Nout, (long long)a.outH * a.outW, a.a0.B);
   }
   // y = conv(x) (+bias) (+temb) (+res) ; out view may be a channel slice
   void conv(const View& x, const PackedWeight& w, const View& out, int stride = 1, int pad = -1, const View* res = nullptr,
@@ -206,6 +227,22 @@ struct Ctx {
     a.out = out.p; a.out_ld = out.ld;
     a.act = act;
     conv(a);
+  }
+  // y = conv3x3(upsample2x(x)) without the upsampled tensor: one 2x2 conv per output parity, each writing every other
+  // pixel of y through a strided TMA store map
+  void upconv(const View& x, const UpConvW& w, const View& y) {
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      ConvArgs a;
+      a.a0 = x;
+      a.w = &w.cls[cls];
+      a.pad_t = 1 - py; a.pad_l = 1 - px;
+      a.outH = x.H; a.outW = x.W;
+      a.out = y.p + ((long long)py * y.W + px) * y.ld;
+      a.out_ld = y.ld;
+      a.out_step = 2;
+      conv(a);
+    }
   }
   void groupnorm(const View& x, const NormW& n, bool silu, const View& y) {
     ++launches;
@@ -230,10 +267,6 @@ struct Ctx {
     snprintf(buf, sizeof buf, "B%d h%d Nq%d Nk%d d%d", a.B, a.heads, a.Nq, a.Nk, a.d);
     traced("attn", buf, 4.0 * a.B * a.heads * (double)a.Nq * a.Nk * a.d,
            2.0 * a.B * a.heads * a.d * (2.0 * a.Nq + 2.0 * a.Nk), [&] { launch_attn(st, a); });
-  }
-  void upsample2x(const View& x, const View& y) {
-    ++launches;
-    if (!dry && !(skip_mask() & SKIP_MISC)) launch_upsample2x(st, x, y.p);
   }
   void add_inplace(const View& y, const bf16* c) {
     ++launches;
@@ -341,6 +374,25 @@ struct WeightStore {
     pack_into(pw.w, pw.N, pw.K, 0, 0, *w, row_map, scale);
     if (b) pw.bias = pack_vec(*b, row_map, scale);
     return pw;
+  }
+  UpConvW upconv(const std::string& key) {
+    UpConvW u;
+    const RawTensor* w = find(key + ".weight");
+    const RawTensor* b = find(key + ".bias");
+    if (!w || !b) return u;
+    SDTF_CHECK(w->shape.size() == 4 && w->shape[2] == 3 && w->shape[3] == 3, key + ": the upsampler convolution must be 3x3");
+    const int O = (int)w->shape[0], I = (int)w->shape[1], Kp = (I + 7) / 8 * 8;
+    bf16* d = (bf16*)pool.alloc((size_t)16 * O * Kp * 2);
+    SDTF_CUDA(cudaMemsetAsync(d, 0, (size_t)16 * O * Kp * 2, st));
+    pack_upconv_kernel<<<148 * 8, 256, 0, st>>>(w->p, O, I, Kp, d);
+    SDTF_CUDA(cudaGetLastError());
+    float* bias = pack_vec(*b, nullptr, 1.f);
+    for (int c = 0; c < 4; ++c) {
+      u.cls[c].w = d + (size_t)c * 4 * O * Kp;
+      u.cls[c].bias = bias;
+      u.cls[c].N = O; u.cls[c].K = Kp; u.cls[c].kh = u.cls[c].kw = 2;
+    }
+    return u;
   }
   NormW norm(const std::string& key) {
     NormW n;

@@ -31,6 +31,7 @@ struct ConvArgs {
   long long res_ld = 0;
   void* out = nullptr;
   long long out_ld = 0;
+  int out_step = 1;  // > 1: output pixel (y, x) of this launch is pixel (step y, step x) of the tensor at `out` (see upconv)
   bool out_fp32 = false;
   int act = ACT_NONE;
   float out_scale = 1.f;
@@ -250,7 +251,7 @@ inline void init_gemm_kernels() {
 // floats of split-K scratch launch_conv would use for this conv (0: the layer is not split)
 inline size_t conv_splitk_floats(const ConvArgs& a) {
   const PackedWeight& w = *a.w;
-  if (a.out_fp32 || a.force_v1 || a.force_bn || gemm_v1_forced()) return 0;
+  if (a.out_fp32 || a.force_v1 || a.force_bn || gemm_v1_forced() || a.out_step != 1) return 0;
   const TileShape ts = choose_tile(a.outW, a.outH, a.a0.B);
   const long long m_tiles = (long long)ceil_div(a.outW, ts.bw) * ceil_div(a.outH, ts.bh) * ceil_div(a.a0.B, ts.bn);
   const int iters = w.kh * w.kw * (ceil_div(a.a0.C, 64) + (a.a1.p ? ceil_div(a.a1.C, 64) : 0));
@@ -342,7 +343,7 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       CUtensorMap tmA0 = make_act_tmap(a.a0, p.bw, p.bh, p.bn, a.stride);
       CUtensorMap tmA1 = a.a1.p ? make_act_tmap(a.a1, p.bw, p.bh, p.bn, a.stride) : tmA0;
       CUtensorMap tmB = make_weight_tmap(w.w, w.K, w.N, p.taps, p.BN / plan.n_mma / cg);
-      CUtensorMap tmOut = make_epi_tmap(reinterpret_cast<const bf16*>(a.out), Nout, p.W, p.H, p.B, a.out_ld, p.bw, p.bh, p.bn);
+      CUtensorMap tmOut = make_epi_tmap(reinterpret_cast<const bf16*>(a.out), Nout, p.W, p.H, p.B, a.out_ld, p.bw, p.bh, p.bn, a.out_step);
       CUtensorMap tmRes = (a.res && !split) ? make_epi_tmap(a.res, Nout, p.W, p.H, p.B, a.res_ld, p.bw, p.bh, p.bn) : tmOut;
       const long long units = ((m_tiles + cg - 1) / cg) * n_tiles * x.splits;
       const long long slots = sm_count() / cg;
@@ -390,6 +391,7 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   }
 
   // ---- one tile per CTA (gemm.cuh): fp32 outputs, unaligned views ----
+  SDTF_CHECK(a.out_step == 1, "conv: strided output needs the TMA-store kernel (bf16, 16-byte aligned output)");
   p.BN = a.force_bn ? a.force_bn : choose_bn(w.N, m_tiles, a.act);
   if (geglu) SDTF_CHECK(w.geglu_half * 2 == p.BN && w.N % p.BN == 0, "GEGLU weight packing must match BN");
   SDTF_CHECK(p.BN % 16 == 0 && p.BN >= 16 && p.BN <= 256, "BN must be a multiple of 16 in [16,256]");

@@ -46,7 +46,7 @@ struct UNetW {
   EncoderHalfW enc;
   ResW up_res[12];
   AttnW up_attn[9];  // output_blocks 3..11
-  PackedWeight up_conv[3];
+  UpConvW up_conv[3];
   NormW out_norm;
   PackedWeight conv_out;
 };
@@ -65,7 +65,8 @@ struct VaeAttnW {
 };
 struct VaeDecW {
   bool ready = false;
-  PackedWeight post_quant, conv_in, conv_out, up_conv[3];
+  PackedWeight post_quant, conv_in, conv_out;
+  UpConvW up_conv[3];
   ResW mid0, mid1, up[4][3];
   VaeAttnW attn;
   NormW out_norm;
@@ -204,7 +205,7 @@ inline void build_unet(WeightStore& ws, UNetW& u) {
       u.up_attn[ai++] = build_attn(ws, b + ".1", kDecCout[i]);
       j = 2;
     }
-    if (i == 2 || i == 5 || i == 8) u.up_conv[ui++] = ws.conv(b + "." + std::to_string(j) + ".conv");
+    if (i == 2 || i == 5 || i == 8) u.up_conv[ui++] = ws.upconv(b + "." + std::to_string(j) + ".conv");
   }
   u.out_norm = ws.norm(p + ".out.0");
   u.conv_out = ws.conv(p + ".out.2");
@@ -248,7 +249,7 @@ inline void build_vae_decoder(WeightStore& ws, VaeDecW& d) {
     for (int r = 0; r < 3; ++r)
       d.up[b][r] = build_res(ws, "decoder.up_blocks." + std::to_string(b) + ".resnets." + std::to_string(r),
                              r == 0 ? kVaeDecCin[b] : kVaeDecCout[b], kVaeDecCout[b], false);
-    if (b < 3) d.up_conv[b] = ws.conv("decoder.up_blocks." + std::to_string(b) + ".upsamplers.0.conv");
+    if (b < 3) d.up_conv[b] = ws.upconv("decoder.up_blocks." + std::to_string(b) + ".upsamplers.0.conv");
   }
   d.out_norm = ws.norm("decoder.conv_norm_out");
   d.conv_out = ws.conv("decoder.conv_out");
@@ -459,11 +460,7 @@ inline void unet_forward(Ctx& c, const UNetW& u, const bf16* latent8, int B, int
     } else {
       res_block(c, rw, cat[i], stage_out, tab, tl);
     }
-    if (up) {  // Upsamplers (diffusion_model.py:132-139)
-      View big = c.alloc_view(B, 2 * cat[i].H, 2 * cat[i].W, rw.cout);
-      c.upsample2x(stage_out, big);
-      c.conv(big, u.up_conv[ui++], dst);
-    }
+    if (up) c.upconv(stage_out, u.up_conv[ui++], dst);  // Upsamplers (diffusion_model.py:132-139), upsample folded into the conv
     c.ws->release(m);
   }
   View t = c.alloc_view(B, h, w, 320);
@@ -584,11 +581,9 @@ inline void vae_decode(Ctx& c, const VaeDecW& d, const float* latent, int B, int
     res_block(c, d.up[b][2], b2, a, nullptr, 0);
     x = a;
     if (b < 3) {
-      View big = c.alloc_view(B, 2 * H, 2 * W, co);
-      c.upsample2x(x, big);
       H *= 2; W *= 2;
       View n = c.alloc_view(B, H, W, co);
-      c.conv(big, d.up_conv[b], n);
+      c.upconv(x, d.up_conv[b], n);  // UpSampling2D(2) + PaddedConv2D(3) (image_decoder.py:36-47), upsample folded into the conv
       x = n;
     }
   }

@@ -273,7 +273,23 @@ inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, 
   if (by > x.B) by = x.B;
   SDTF_CHECK(by >= 1, "GroupNorm: a sample's CTAs do not fit on the device at once");
   dim3 grid((unsigned)nblk, (unsigned)by);
-  launch_pdl(gn_fused_kernel, grid, dim3(threads), smem, st, 1, x.p, x.ld, x.C, HW, (int)ppc, x.B, sc, gamma, beta, silu ? 1 : 0, y, ldy);
+  // The per-sample barrier needs every CTA of the grid resident at once.  A COOPERATIVE launch makes that the driver's
+  // promise instead of an assumption about what else runs on the device: if another stream / process / engine holds
+  // SMs, the launch is refused (cudaErrorCooperativeLaunchTooLarge) or waits for room — it can no longer start with
+  // part of the grid and spin.  (SDTF_GN_COOP=0: plain launch, for A/B timing.)
+  static const int coop = getenv("SDTF_GN_COOP") ? atoi(getenv("SDTF_GN_COOP")) : 1;
+  if (coop && !pdl_enabled()) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SDTF_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const bf16*)x.p, (long long)x.ld, x.C, HW, (int)ppc, x.B, sc, gamma, beta,
+                                 silu ? 1 : 0, y, ldy));
+  } else {
+    launch_pdl(gn_fused_kernel, grid, dim3(threads), smem, st, 1, x.p, x.ld, x.C, HW, (int)ppc, x.B, sc, gamma, beta, silu ? 1 : 0, y, ldy);
+  }
   SDTF_CUDA(cudaGetLastError());
   return 1;
 }
@@ -428,30 +444,6 @@ inline void launch_layernorm(cudaStream_t st, const bf16* x, long long ld, int C
     else if (vecs <= 96) layernorm_kernel<3><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
     else layernorm_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(x, ld, C, rows, gamma, beta, y, ldy);
   }
-  SDTF_CUDA(cudaGetLastError());
-}
-
-// ------------------------------------------------------------------------------------------------------
-// nearest 2x upsample (UpSampling2D(2): diffusion_model.py:135, image_decoder.py:36,41,46)
-// ------------------------------------------------------------------------------------------------------
-__global__ void upsample2x_kernel(const bf16* __restrict__ x, long long ld, int B, int H, int W, int C, bf16* __restrict__ y) {
-  const int vecs = C >> 3;
-  const long long total = (long long)B * (2 * H) * (2 * W) * vecs;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % vecs);
-    long long p = i / vecs;
-    const int ox = (int)(p % (2 * W)); p /= (2 * W);
-    const int oy = (int)(p % (2 * H));
-    const int b = (int)(p / (2 * H));
-    const uint4 u = *reinterpret_cast<const uint4*>(x + (((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * ld + cv * 8);
-    *reinterpret_cast<uint4*>(y + i * 8) = u;
-  }
-}
-inline void launch_upsample2x(cudaStream_t st, const View& x, bf16* y) {
-  const long long total = (long long)x.B * 4 * x.H * x.W * (x.C / 8);
-  long long blocks = ceil_div_ll(total, 256 * 4);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  upsample2x_kernel<<<(unsigned)blocks, 256, 0, st>>>(x.p, x.ld, x.B, x.H, x.W, x.C, y);
   SDTF_CUDA(cudaGetLastError());
 }
 
@@ -857,6 +849,31 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int I, int tap
     const int so = row_map ? row_map[row] : row;
     const float v = so >= 0 ? src[((long long)so * I + k) * taps + t] * scale : 0.f;
     dst[((long long)t * Ntot + n0 + row) * Kp + k0 + k] = __float2bfloat16(v);
+  }
+}
+
+// Nearest-2x upsample followed by a 3x3 convolution (diffusion_model.py:132-139, image_decoder.py:36-47) == four 2x2
+// convolutions on the SOURCE grid, one per output parity (py, px): output pixel (2y+py, 2x+px) reads source rows
+// {y-1, y} (py = 0) or {y, y+1} (py = 1), and the 3x3 taps that land on the same source pixel are summed:
+//   py = 0: tap row 0 <- k0,      tap row 1 <- k1 + k2        py = 1: tap row 0 <- k0 + k1,  tap row 1 <- k2
+// (columns alike).  4/9 of the multiply-adds, no upsampled tensor.  src fp32 [O][I][3][3] -> dst bf16
+// [class = 2 py + px][tap = 2 r + s][O][Kp], summed in fp32 and rounded once.
+__global__ void pack_upconv_kernel(const float* __restrict__ src, int O, int I, int Kp, bf16* __restrict__ dst) {
+  const long long total = 16LL * O * I;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % I);
+    long long r0 = i / I;
+    const int o = (int)(r0 % O);
+    const int ct = (int)(r0 / O);  // class * 4 + tap
+    const int py = ct >> 3, px = (ct >> 2) & 1, r = (ct >> 1) & 1, sc = ct & 1;
+    // 3x3 rows merged into 2x2 row r of parity py: [lo, hi]
+    const int ylo = py == 0 ? (r == 0 ? 0 : 1) : (r == 0 ? 0 : 2), yhi = py == 0 ? (r == 0 ? 0 : 2) : (r == 0 ? 1 : 2);
+    const int xlo = px == 0 ? (sc == 0 ? 0 : 1) : (sc == 0 ? 0 : 2), xhi = px == 0 ? (sc == 0 ? 0 : 2) : (sc == 0 ? 1 : 2);
+    const float* w = src + ((long long)o * I + k) * 9;
+    float acc = 0.f;
+    for (int y = ylo; y <= yhi; ++y)
+      for (int x = xlo; x <= xhi; ++x) acc += w[y * 3 + x];
+    dst[((long long)ct * O + o) * Kp + k] = __float2bfloat16(acc);
   }
 }
 

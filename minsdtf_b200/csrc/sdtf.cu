@@ -720,7 +720,7 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
   const std::string key = std::to_string(B) + "x" + std::to_string(h) + "x" + std::to_string(w) + "x" + std::to_string(T) + "x" +
                           std::to_string(Tu) + (cfg ? (split ? (srank ? "S" : "s") : (two_pass ? "t" : "c")) : "-") +
                           (control ? "n" : "-") + (inpaint ? "m" : "-") + (d->step_noise ? "z" : "-") + "s" + std::to_string(S);
-  const bool use_graph = d->use_cuda_graph != 0;
+  const bool use_graph = d->use_cuda_graph != 0 && !trace_on();  // per-operator events need eager launches
 
   e->run_sized([&](Ctx& c) {
     // ---- job-resident buffers (same addresses for the same configuration => the captured graph stays valid) ----
@@ -964,6 +964,28 @@ int sdtf_get_timings(const sdtf_engine* e, sdtf_timings* out) {
   if (!e || !out) return SDTF_ERR_INVALID;
   *out = e->timings;
   return SDTF_OK;
+}
+
+int sdtf_trace_begin(sdtf_engine* e) {
+  SDTF_API_BEGIN
+  SDTF_CUDA(cudaStreamSynchronize(e->st));
+  TraceTotals& t = trace_totals();
+  t = TraceTotals();
+  t.collecting = true;
+  t.quiet = getenv("SDTF_TRACE") == nullptr;
+  SDTF_API_END
+}
+
+int sdtf_trace_end(sdtf_engine* e, sdtf_trace_summary* out) {
+  SDTF_API_BEGIN
+  SDTF_CHECK(out != nullptr, "out is NULL");
+  SDTF_CUDA(cudaStreamSynchronize(e->st));
+  TraceTotals& t = trace_totals();
+  for (int k = 0; k < 4; ++k) {
+    out->launches[k] = t.launches[k]; out->us[k] = t.us[k]; out->flop[k] = t.flop[k]; out->bytes[k] = t.bytes[k];
+  }
+  t.collecting = false;
+  SDTF_API_END
 }
 
 int sdtf_bench_conv(sdtf_engine* e, int32_t batch, int32_t hw, int32_t cin, int32_t cout, int32_t ksize, int32_t reps,

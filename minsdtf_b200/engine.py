@@ -301,6 +301,16 @@ class Engine:
         self._check(self._lib.sdtf_get_timings(self._h, ctypes.byref(t)))
         return {"loop_ms": t.loop_ms, "decode_ms": t.decode_ms, "total_ms": t.total_ms, "kernel_launches": t.kernel_launches}
 
+    def trace_begin(self):
+        """Start per-operator-class accounting (eager launches bracketed by CUDA events; see include/sdtf.h)."""
+        self._check(self._lib.sdtf_trace_begin(self._h))
+
+    def trace_end(self) -> dict:
+        t = _lib.TraceSummary()
+        self._check(self._lib.sdtf_trace_end(self._h, ctypes.byref(t)))
+        return {k: {"launches": int(t.launches[i]), "us": float(t.us[i]), "flop": float(t.flop[i]), "bytes": float(t.bytes[i])}
+                for i, k in enumerate(("conv", "attn", "gn", "ln"))}
+
     def bench_attention(self, batch, heads, nq, nk, d, reps=20, legacy=False) -> float:
         ms = ctypes.c_float()
         self._check(self._lib.sdtf_bench_attention(self._h, batch, heads, nq, nk, d, reps, int(legacy), ctypes.byref(ms)))

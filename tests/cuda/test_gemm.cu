@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "gemm_host.cuh"
+#include "ops.cuh"
 
 using namespace sdtf;
 
@@ -279,6 +280,79 @@ static bool check_batch_invariance(int B, int HW, int C, int N, bool temb, bool 
   return diff == 0;
 }
 
+// Nearest-2x upsample + 3x3 conv folded into four 2x2 parity convolutions (engine.cuh Ctx::upconv, ops.cuh
+// pack_upconv_kernel) against the naive definition: upsample, zero-pad, 3x3 conv with the fp32 weights.
+__global__ void ref_upconv(const bf16* x, int B, int H, int W, int C, const float* w /* [N][C][3][3] */, const float* bias, int N,
+                           float* out /* [B][2H][2W][N] */) {
+  const long long total = (long long)B * 4 * H * W * N;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int n = (int)(idx % N);
+  long long pix = idx / N;
+  const int ox = (int)(pix % (2 * W)), oy = (int)((pix / (2 * W)) % (2 * H)), b = (int)(pix / (4LL * H * W));
+  float acc = bias[n];
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      const int uy = oy + r - 1, ux = ox + s - 1;  // coordinates on the upsampled grid
+      if (uy < 0 || uy >= 2 * H || ux < 0 || ux >= 2 * W) continue;
+      const bf16* px = x + (((long long)b * H + (uy >> 1)) * W + (ux >> 1)) * C;
+      for (int k = 0; k < C; ++k) acc += __bfloat162float(px[k]) * w[((long long)n * C + k) * 9 + r * 3 + s];
+    }
+  out[idx] = acc;
+}
+
+static bool check_upconv(int B, int H, int W, int C, int N, int ld_extra) {
+  std::vector<float> h((size_t)B * H * W * C);
+  for (auto& v : h) v = frand();
+  bf16* x = upload_bf16(h);
+  h.resize((size_t)N * C * 9);
+  const float ws = 1.f / sqrtf((float)C * 9);
+  for (auto& v : h) v = frand() * ws * 1.7f;
+  float* w = upload_f32(h);
+  h.resize(N);
+  for (auto& v : h) v = frand();
+  float* bias = upload_f32(h);
+  bf16* packed = dalloc<bf16>((size_t)16 * N * C);
+  pack_upconv_kernel<<<148 * 4, 256>>>(w, N, C, C, packed);
+  const long long opix = (long long)B * 4 * H * W, ld = N + ld_extra;
+  bf16* out = dalloc<bf16>(opix * ld);
+  SDTF_CUDA(cudaMemset(out, 0, opix * ld * 2));
+  PackedWeight pw[4];
+  for (int cls = 0; cls < 4; ++cls) {
+    pw[cls].w = packed + (size_t)cls * 4 * N * C; pw[cls].bias = bias; pw[cls].N = N; pw[cls].K = C; pw[cls].kh = pw[cls].kw = 2;
+    ConvArgs a;
+    a.a0 = View{x, B, H, W, C, C};
+    a.w = &pw[cls];
+    a.pad_t = 1 - (cls >> 1); a.pad_l = 1 - (cls & 1);
+    a.outH = H; a.outW = W;
+    a.out = out + ((long long)(cls >> 1) * 2 * W + (cls & 1)) * ld; a.out_ld = ld; a.out_step = 2;
+    launch_conv(0, a);
+  }
+  float* ref = dalloc<float>(opix * N);
+  ref_upconv<<<(unsigned)((opix * N + 255) / 256), 256>>>(x, B, H, W, C, w, bias, N, ref);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("CASE upconv  CUDA ERROR: %s\n", cudaGetErrorString(e)); exit(3); }
+  std::vector<float> hr(opix * N);
+  std::vector<bf16> ho(opix * ld);
+  SDTF_CUDA(cudaMemcpy(hr.data(), ref, hr.size() * 4, cudaMemcpyDeviceToHost));
+  SDTF_CUDA(cudaMemcpy(ho.data(), out, ho.size() * 2, cudaMemcpyDeviceToHost));
+  long long bad = 0, pad_bad = 0;
+  double max_err = 0;
+  for (long long p = 0; p < opix; ++p) {
+    for (int n = 0; n < N; ++n) {
+      const double r = hr[p * N + n], o = __bfloat162float(ho[p * ld + n]), err = fabs(r - o);
+      if (!(err <= 1e-2 * (1.0 + fabs(r)))) ++bad;
+      if (err > max_err) max_err = err;
+    }
+    for (int n = N; n < ld; ++n)
+      if (__bfloat162float(ho[p * ld + n]) != 0.f) ++pad_bad;
+  }
+  printf("CASE upconv B%d %dx%d->%dx%d %d->%d ldx%d  %s  max_err %.4g bad %lld pad_bad %lld\n", B, H, W, 2 * H, 2 * W, C, N, ld_extra,
+         bad == 0 && pad_bad == 0 ? "OK  " : "FAIL", max_err, bad, pad_bad);
+  cudaFree(x); cudaFree(w); cudaFree(bias); cudaFree(packed); cudaFree(out); cudaFree(ref);
+  return bad == 0 && pad_bad == 0;
+}
+
 int main(int argc, char** argv) {
   bool bench = argc > 1 && !strcmp(argv[1], "bench");
   const char* only = argc > 2 ? argv[2] : nullptr;  // bench <substr>: run only the benchmark cases whose name contains substr
@@ -344,6 +418,10 @@ int main(int argc, char** argv) {
       fails += check_batch_invariance(16, 8, 1280, 1280, false, true) ? 0 : 1;
       fails += check_batch_invariance(3, 4, 1280, 640, true, true) ? 0 : 1;
       fails += check_batch_invariance(2, 16, 640, 640, false, false) ? 0 : 1;  // not split: the plain schedule
+      fails += check_upconv(2, 8, 8, 128, 128, 0) ? 0 : 1;
+      fails += check_upconv(1, 16, 16, 320, 320, 64) ? 0 : 1;   // output is a channel slice of a wider buffer
+      fails += check_upconv(3, 12, 20, 64, 96, 0) ? 0 : 1;      // ragged tiles, rectangular
+      fails += check_upconv(1, 64, 64, 256, 256, 0) ? 0 : 1;    // VAE-sized grid
     }
     if (bench)
       for (auto& c : bench_cases)
