@@ -1182,6 +1182,277 @@ constexpr size_t xattn_smem_bytes() {
   return 1024 + (size_t)(2 * DCH + QST * DCH + 4) * 128 * 128 + 1024 + 8 + 16 * QST + 80 + 16;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// vattn: the VAE mid-block AttentionBlock (layers.py:28-59) as a flash kernel — ONE head of size 512, N = H*W tokens
+// (4096 at 512x512, 9216 at 768x768), softmax(Q K^T / sqrt(512)) V + b_v.  The reference materialises the N x N
+// score matrix (layers.py:46-50); round 1 of this engine did too (3 GEMMs + a row softmax per sample, 100 MB of fp32
+// scores per sample at 512x512, 510 MB at 768x768).  Here nothing of size N x N exists:
+//   * a CTA owns 128 query rows and ONE HALF (256 columns) of the output: TMEM holds two S buffers (2 x 128 columns)
+//     and the 128 x 256 fp32 accumulator — exactly the 512 columns there are;
+//   * Q (8 chunks of 64 columns, 128 KB) stays in shared memory; K and V stream through a 4-slot ring of 16 KB chunks in
+//     the order the tensor core consumes them: K_0 | K_1 V_0 | K_2 V_1 | ... (K tile: 8 chunks, V half tile: 4 chunks);
+//   * warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax (a thread owns a query row) and epilogue.  S is double
+//     buffered, so Q K_{j+1}^T runs while the softmax of tile j is computed; P V_j follows it on the tensor pipe.
+// Tensor work per key tile: 2048 + 1024 cycles against ~1100 cycles of softmax: tensor / operand-delivery bound.
+// ------------------------------------------------------------------------------------------------------
+static constexpr int kVAThreads = 192;
+static constexpr int kVARing = 4;
+
+struct VAttnParams {
+  int N;             // tokens per sample (queries == keys)
+  float scale_log2;  // 512^-1/2 * log2(e)
+  const float* v_bias;  // [512] added after the attention (rows of softmax sum to 1), may be null
+  bf16* out;         // [B*N][ldo]
+  long long ldo;
+};
+
+__global__ void __launch_bounds__(kVAThreads, 1)
+vattn_kernel(const __grid_constant__ CUtensorMap tmQKV, const VAttnParams p) {
+  using namespace tc05;
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kChunk = 128 * 128;  // [128 rows][64 bf16] swizzled = 16 KB
+  constexpr int D = 512, QCH = D / 64, VCH = 4;  // Q / K chunks per tile, V chunks per half tile
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;                       // 8 chunks
+  const uint32_t sR = sQ + QCH * kChunk;          // ring: kVARing chunks
+  const uint32_t sP = sR + kVARing * kChunk;      // 2 chunks (128 rows x 128 keys)
+  const uint32_t bars = sP + 2 * kChunk;
+  const uint32_t q_full = bars;
+  auto r_full = [&](int s) { return bars + 8u + 8u * s; };
+  auto r_empty = [&](int s) { return bars + 8u + 8u * (kVARing + s); };
+  const uint32_t bb = bars + 8u + 16u * kVARing;
+  auto s_full = [&](int i) { return bb + 8u * i; };
+  auto s_free = [&](int i) { return bb + 16u + 8u * i; };
+  const uint32_t p_full = bb + 32u, o_done = bb + 40u;
+  const uint32_t tmem_slot = bb + 48u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, half = blockIdx.y, b = blockIdx.z;
+  const int nkv = (p.N + 127) / 128;
+  auto keys_in_tile = [&](int j) {
+    int n = p.N - j * 128;
+    n = n > 128 ? 128 : n;
+    return (n + 15) & ~15;
+  };
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQKV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < kVARing; ++s) { mbar_init(r_full(s), 1); mbar_init(r_empty(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(s_full(i), 1); mbar_init(s_free(i), 4); }
+    mbar_init(p_full, 4);
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();  // q | k | v come from the projection GEMM
+
+  if (warp == 0) {
+    // ===== TMA producer: Q once, then the chunk stream K_0 | K_1 V_0 | ... | K_{n-1} V_{n-2} | V_{n-1} =====
+    if (elect_one()) {
+      mbar_expect_tx(q_full, QCH * kChunk);
+#pragma unroll
+      for (int c = 0; c < QCH; ++c) tma_load_3d(sQ + c * kChunk, &tmQKV, q_full, 64 * c, q0, b);
+      uint32_t slot = 0, ph = 0;
+      auto push = [&](int col, int row) {
+        mbar_wait(r_empty(slot), ph ^ 1u);
+        mbar_expect_tx(r_full(slot), kChunk);
+        tma_load_3d(sR + slot * kChunk, &tmQKV, r_full(slot), col, row, b);
+        if (++slot == kVARing) { slot = 0; ph ^= 1u; }
+      };
+      for (int j = 0; j <= nkv; ++j) {
+        if (j < nkv)
+          for (int c = 0; c < QCH; ++c) push(D + 64 * c, j * 128);                          // K_j
+        if (j >= 1)
+          for (int c = 0; c < VCH; ++c) push(2 * D + half * 256 + 64 * c, (j - 1) * 128);   // V_{j-1}, this CTA's half
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (elect_one()) {
+      const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);  // B = V chunk is MN-major
+      const uint64_t dp = make_smem_desc_sw128(sP, 16, 1024);
+      uint32_t slot = 0, ph = 0;
+      mbar_wait(q_full, 0);
+      for (int j = 0; j <= nkv; ++j) {
+        if (j < nkv) {
+          const int sb = j & 1;
+          if (j >= 2) mbar_wait(s_free(sb), (uint32_t)((j >> 1) - 1) & 1u);  // S of tile j-2 is in registers
+          fence_after_sync();
+          const uint32_t idesc = make_idesc_bf16(128, keys_in_tile(j), 0, 0);
+          for (int c = 0; c < QCH; ++c) {
+            mbar_wait(r_full(slot), ph);
+            fence_after_sync();
+            const uint64_t dq = make_smem_desc_sw128(sQ + c * kChunk, 16, 1024);
+            const uint64_t dk = make_smem_desc_sw128(sR + slot * kChunk, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_f16_ss(tmem + 128u * sb, dq + 2 * k, dk + 2 * k, idesc, (c | k) != 0);
+            mma_commit(r_empty(slot));
+            if (++slot == kVARing) { slot = 0; ph ^= 1u; }
+          }
+          mma_commit(s_full(sb));
+        }
+        if (j >= 1) {
+          const int jj = j - 1;
+          mbar_wait(p_full, (uint32_t)jj & 1u);  // P_jj is in shared memory (and the accumulator has been rescaled if needed)
+          fence_after_sync();
+          const int ksteps = keys_in_tile(jj) >> 4;
+          for (int c = 0; c < VCH; ++c) {
+            mbar_wait(r_full(slot), ph);
+            fence_after_sync();
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t da = dp + (uint64_t)((k >> 2) * (kChunk >> 4) + (k & 3) * 2);
+              const uint64_t db = make_smem_desc_sw128(sR + slot * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
+              mma_f16_ss(tmem + 256u + 64u * c, da, db, idesc_pv, (jj | k) != 0);
+            }
+            mma_commit(r_empty(slot));
+            if (++slot == kVARing) { slot = 0; ph ^= 1u; }
+          }
+          mma_commit(o_done);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===== softmax + epilogue: thread = query row =====
+    const int quad = warp & 3;  // a warp reaches TMEM lanes [32 (warp % 4), +32): warps 2..5 own quadrants 2, 3, 0, 1
+    const int row = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const int sw = row & 7;
+    uint8_t* rowp = gen + (sP - base) + row * 128;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < nkv; ++j) {
+      const int sb = j & 1;
+      const int nvalid = min(128, p.N - j * 128);
+      mbar_wait(s_full(sb), (uint32_t)(j >> 1) & 1u);
+      fence_after_sync();
+      uint32_t sv[128];
+      const uint32_t tS = tmem + 128u * sb + lane_off;
+      tmem_ld32_at<0>(tS, sv);
+      tmem_ld32_at<32>(tS + 32, sv);
+      tmem_ld32_at<64>(tS + 64, sv);
+      tmem_ld32_at<96>(tS + 96, sv);
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_free(sb));
+      if (nvalid < 128) {
+#pragma unroll
+        for (int i = 0; i < 128; ++i)
+          if (i >= nvalid) sv[i] = 0xff800000u;  // -inf
+      }
+      float mx = fmax3(__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]));
+      float mx2 = fmax3(__uint_as_float(sv[3]), __uint_as_float(sv[4]), __uint_as_float(sv[5]));
+#pragma unroll
+      for (int i = 6; i + 3 < 128; i += 4) {
+        mx = fmax3(mx, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        mx2 = fmax3(mx2, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+      }
+      mx = fmax3(mx, mx2, fmaxf(__uint_as_float(sv[126]), __uint_as_float(sv[127])));
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const bool grow = (m_new - m_run) > 8.f;  // the running max only moves when it grows by more than 2^8 (see attn2q)
+      if (j > 0) {  // P V_{j-1} complete: P may be overwritten, the accumulator may be rescaled
+        mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
+        fence_after_sync();
+      }
+      if (__any_sync(0xffffffffu, grow)) {
+        const float alpha = grow ? ex2f(m_run - m_new) : 1.f;
+        if (grow) { m_run = m_new; l_run *= alpha; }
+        if (j > 0) {
+#pragma unroll 4
+          for (int c = 0; c < 256; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem + 256u + lane_off + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(tmem + 256u + lane_off + c, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;
+      float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 128; c += 8) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) e[i] = ex2f(fmaf(__uint_as_float(sv[c + i]), p.scale_log2, neg_m));
+        ls0 += (e[0] + e[1]) + (e[2] + e[3]);
+        ls1 += (e[4] + e[5]) + (e[6] + e[7]);
+        uint4 w;
+        w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]);
+        w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
+        const int chunk = c >> 6, un = (c & 63) >> 3;
+        *reinterpret_cast<uint4*>(rowp + chunk * kChunk + ((un ^ sw) << 4)) = w;
+      }
+      l_run += ls0 + ls1;
+      fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l + b_v -> bf16 ----
+    mbar_wait(o_done, (uint32_t)(nkv - 1) & 1u);
+    fence_after_sync();
+    const float inv_l = 1.f / l_run;
+    const int q = q0 + row;
+    const bool ok = q < p.N;
+    bf16* orow = p.out + ((long long)b * p.N + q) * p.ldo + half * 256;
+    const float* vb = p.v_bias ? p.v_bias + half * 256 : nullptr;
+#pragma unroll 2
+    for (int c = 0; c < 256; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem + 256u + lane_off + c, v);
+      tmem_ld_wait();
+      float o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(v[i]) * inv_l + (vb ? __ldg(vb + c + i) : 0.f);
+      if (ok) {
+        uint4 w0, w1;
+        w0.x = pack_bf16(o[0], o[1]);   w0.y = pack_bf16(o[2], o[3]);
+        w0.z = pack_bf16(o[4], o[5]);   w0.w = pack_bf16(o[6], o[7]);
+        w1.x = pack_bf16(o[8], o[9]);   w1.y = pack_bf16(o[10], o[11]);
+        w1.z = pack_bf16(o[12], o[13]); w1.w = pack_bf16(o[14], o[15]);
+        *reinterpret_cast<uint4*>(orow + c) = w0;
+        *reinterpret_cast<uint4*>(orow + c + 8) = w1;
+      }
+      __syncwarp();
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+constexpr size_t vattn_smem_bytes() { return 1024 + (size_t)(8 + kVARing + 2) * 128 * 128 + 8 + 16 * kVARing + 48 + 16 + 16; }
+
+// qkv: [B][N][ld] bf16 with q at column 0, k at 512, v at 1024; out: [B][N][ldo] (512 columns)
+inline void launch_vattn(cudaStream_t stream, const bf16* qkv, long long ld, int B, int N, const float* v_bias, bf16* out, long long ldo) {
+  static_assert(vattn_smem_bytes() <= 232448, "vattn must fit 227 KB of shared memory");
+  VAttnParams p;
+  p.N = N;
+  p.scale_log2 = (float)(1.4426950408889634 / sqrt(512.0));
+  p.v_bias = v_bias;
+  p.out = out; p.ldo = ldo;
+  uint64_t dims[3] = {1536, (uint64_t)N, (uint64_t)B};
+  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)N * ld * 2};
+  uint32_t box[3] = {64, 128, 1};
+  uint32_t es[3] = {1, 1, 1};
+  CUtensorMap tm = make_tmap_bf16(qkv, 3, dims, strides, box, es);
+  dim3 grid((unsigned)ceil_div(N, 128), 2, (unsigned)B);
+  launch_pdl(vattn_kernel, grid, dim3(kVAThreads), vattn_smem_bytes(), stream, 1, tm, p);
+  SDTF_CUDA(cudaGetLastError());
+}
+
 // Q/K/V token matrices: [B][N][ld] bf16; head h of Q at q + h*dstride etc.
 struct AttnArgs {
   const bf16 *q, *k, *v;
@@ -1220,6 +1491,7 @@ inline void init_attn_kernels() {
   SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
   init_attn_t<2, 5, 80, 2, 2>();
   init_attn_t<3, 10, 160, 1, 1>();
+  SDTF_CUDA(cudaFuncSetAttribute(vattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vattn_smem_bytes()));
   static_assert(xattn_smem_bytes<2, 3>() <= 232448, "d = 80 cross-attention must fit 227 KB of shared memory");
   SDTF_CUDA(cudaFuncSetAttribute(xattn_kernel<1, 3, 48, 4, 80>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem_bytes<1, 4>()));
   SDTF_CUDA(cudaFuncSetAttribute(xattn_kernel<1, 3, 48, 4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xattn_smem_bytes<1, 4>()));

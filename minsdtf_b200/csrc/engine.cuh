@@ -268,6 +268,15 @@ struct Ctx {
     traced("attn", buf, 4.0 * a.B * a.heads * (double)a.Nq * a.Nk * a.d,
            2.0 * a.B * a.heads * a.d * (2.0 * a.Nq + 2.0 * a.Nk), [&] { launch_attn(st, a); });
   }
+  // VAE mid-block attention: qkv (B, N, 1536) -> o (B, N, 512)
+  void vattn(const View& qkv, int N, const float* v_bias, const View& o) {
+    ++launches;
+    if (dry || (skip_mask() & SKIP_ATTN)) return;
+    char buf[64];
+    snprintf(buf, sizeof buf, "B%d h1 Nq%d Nk%d d512", qkv.B, N, N);
+    traced("attn", buf, 4.0 * qkv.B * (double)N * N * 512, 2.0 * qkv.B * N * 512 * 4.0,
+           [&] { launch_vattn(st, qkv.p, qkv.ld, qkv.B, N, v_bias, o.p, o.ld); });
+  }
   void add_inplace(const View& y, const bf16* c) {
     ++launches;
     if (dry) return;

@@ -60,8 +60,8 @@ struct ControlNetW {
 
 struct VaeAttnW {
   NormW gn;
-  PackedWeight q, k, v, proj;  // v: no bias inside (bias moved after the attention, rows of softmax sum to 1)
-  float* v_bias = nullptr;
+  PackedWeight qkv, proj;  // q | k | v stacked along N (bias on the q and k rows only)
+  float* v_bias = nullptr; // added after the attention (rows of softmax sum to 1)
 };
 struct VaeDecW {
   bool ready = false;
@@ -225,11 +225,17 @@ inline void build_controlnet(WeightStore& ws, ControlNetW& c) {
 inline VaeAttnW build_vae_attn(WeightStore& ws, const std::string& p) {
   VaeAttnW a;
   a.gn = ws.norm(p + ".group_norm");
-  a.q = ws.conv(p + ".query");
-  a.k = ws.conv(p + ".key");
-  a.v = ws.conv(p + ".value", /*bias=*/false);
+  a.qkv = ws.stack({p + ".query", p + ".key", p + ".value"}, 1, 512, 512);
+  const RawTensor* qb = ws.find(p + ".query.bias");
+  const RawTensor* kb = ws.find(p + ".key.bias");
   const RawTensor* vb = ws.find(p + ".value.bias");
-  if (vb) a.v_bias = ws.pack_vec(*vb, nullptr, 1.f);
+  if (qb && kb && vb) {
+    a.qkv.bias = (float*)ws.pool.alloc(1536 * 4);
+    SDTF_CUDA(cudaMemsetAsync(a.qkv.bias, 0, 1536 * 4, ws.st));
+    ws.pack_vec(*qb, nullptr, 1.f, a.qkv.bias, 0);
+    ws.pack_vec(*kb, nullptr, 1.f, a.qkv.bias, 512);
+    a.v_bias = ws.pack_vec(*vb, nullptr, 1.f);
+  }
   a.proj = ws.conv(p + ".proj_attn");
   return a;
 }
@@ -418,32 +424,42 @@ inline void encoder_half(Ctx& c, const EncoderHalfW& e, View* outs /*[12]*/, con
   c.ws->release(m);
 }
 
-// UNet forward.  latent8: (B,h,w,8) bf16 (4 real channels), t_emb (B,320) f32 device, kv: projected context,
-// controls: null or 13 dense bf16 tensors, eps_out: (B,h,w,4) f32.  time_tab: optional precomputed [B][ncat] table of
-// the time-embedding MLP + per-ResBlock projections (the denoise loop computes it for every step before the loop: it
-// depends on the timestep only), in which case t_emb is not read.
-inline void unet_forward(Ctx& c, const UNetW& u, const bf16* latent8, int B, int h, int w, const float* t_emb, const CtxKV& kv,
-                         const bf16* const* controls, float* eps_out, const float* time_tab = nullptr) {
-  const size_t m0 = c.ws->mark();
-  const float* tab = time_tab ? time_tab : time_table(c, u.enc.time, t_emb, B);
-  const int tl = u.enc.time.ncat;
+// UNet forward in two halves, so that ControlNet's zero-convolutions can add their residuals to the skip tensors between
+// them (diffusion_model.py:230-234) from their own epilogue instead of through 13 element-wise kernels.
+struct UNetState {
+  View cat[12];   // concat buffers [x | skip] of the up path
+  View outs[12];  // the 12 skip tensors (channel slices of cat[])
+  View xmid;      // middle-block output (slice of cat[0])
+  const float* tab = nullptr;
+  size_t mark = 0;
+};
+
+// latent8: (B,h,w,8) bf16 (4 real channels), t_emb (B,320) f32 device, kv: projected context.  time_tab: optional
+// precomputed [B][ncat] table of the time-embedding MLP + per-ResBlock projections (the denoise loop computes it for every
+// step before the loop: it depends on the timestep only), in which case t_emb is not read.
+inline void unet_encode(Ctx& c, const UNetW& u, const bf16* latent8, int B, int h, int w, const float* t_emb, const CtxKV& kv,
+                        const float* time_tab, UNetState& s) {
+  s.mark = c.ws->mark();
+  s.tab = time_tab ? time_tab : time_table(c, u.enc.time, t_emb, B);
   // concat buffers cat[i] = [x (cx) | skip (cs)] at the resolution of up block i
   static const int cx[12] = {1280, 1280, 1280, 1280, 1280, 1280, 1280, 640, 640, 640, 320, 320};
   static const int cs[12] = {1280, 1280, 1280, 1280, 1280, 640, 640, 640, 320, 320, 320, 320};
   static const int lvl[12] = {3, 3, 3, 2, 2, 2, 1, 1, 1, 0, 0, 0};
-  View cat[12];
-  for (int i = 0; i < 12; ++i) cat[i] = c.alloc_view(B, h >> lvl[i], w >> lvl[i], cx[i] + cs[i]);
-  View outs[12];
-  for (int k = 0; k < 12; ++k) outs[k] = cat[11 - k].slice(cx[11 - k], cs[11 - k]);
+  for (int i = 0; i < 12; ++i) s.cat[i] = c.alloc_view(B, h >> lvl[i], w >> lvl[i], cx[i] + cs[i]);
+  for (int k = 0; k < 12; ++k) s.outs[k] = s.cat[11 - k].slice(cx[11 - k], cs[11 - k]);
   View lat;
   lat.p = const_cast<bf16*>(latent8); lat.B = B; lat.H = h; lat.W = w; lat.C = 8; lat.ld = 8;
-  c.conv(lat, u.enc.conv_in, outs[0]);
-  View xmid = cat[0].slice(0, 1280);
-  encoder_half(c, u.enc, outs, xmid, tab, tl, kv);
-  if (controls) {  // diffusion_model.py:230-234
-    c.add_inplace(xmid, controls[12]);
-    for (int k = 0; k < 12; ++k) c.add_inplace(outs[k], controls[k]);
-  }
+  c.conv(lat, u.enc.conv_in, s.outs[0]);
+  s.xmid = s.cat[0].slice(0, 1280);
+  encoder_half(c, u.enc, s.outs, s.xmid, s.tab, u.enc.time.ncat, kv);
+}
+
+// up path + output convolution; eps_out: (B,h,w,4) f32.  Releases everything unet_encode allocated.
+inline void unet_decode(Ctx& c, const UNetW& u, int B, int h, int w, const CtxKV& kv, UNetState& s, float* eps_out) {
+  static const int cx[12] = {1280, 1280, 1280, 1280, 1280, 1280, 1280, 640, 640, 640, 320, 320};
+  const int tl = u.enc.time.ncat;
+  const float* tab = s.tab;
+  View* cat = s.cat;
   int ai = 0, ui = 0;
   View final_x = c.alloc_view(B, h, w, 320);
   for (int i = 0; i < 12; ++i) {
@@ -469,7 +485,19 @@ inline void unet_forward(Ctx& c, const UNetW& u, const bf16* latent8, int B, int
   a.a0 = t; a.w = &u.conv_out; a.pad_t = a.pad_l = 1; a.outH = h; a.outW = w;
   a.out = eps_out; a.out_ld = 4; a.out_fp32 = true;
   c.conv(a);
-  c.ws->release(m0);
+  c.ws->release(s.mark);
+}
+
+// DiffusionModel.predict_on_batch (diffusion_model.py:163-283).  controls: null or 13 dense bf16 tensors.
+inline void unet_forward(Ctx& c, const UNetW& u, const bf16* latent8, int B, int h, int w, const float* t_emb, const CtxKV& kv,
+                         const bf16* const* controls, float* eps_out, const float* time_tab = nullptr) {
+  UNetState s;
+  unet_encode(c, u, latent8, B, h, w, t_emb, kv, time_tab, s);
+  if (controls) {  // diffusion_model.py:230-234 with caller-supplied residual tensors
+    c.add_inplace(s.xmid, controls[12]);
+    for (int k = 0; k < 12; ++k) c.add_inplace(s.outs[k], controls[k]);
+  }
+  unet_decode(c, u, B, h, w, kv, s, eps_out);
 }
 
 // HintNet (control_net.py:10-31): image8 (B,H,W,8) bf16 (3 real channels, [0,1]) -> hint (B,H/8,W/8,320) bf16
@@ -487,9 +515,12 @@ inline void hintnet_forward(Ctx& c, const ControlNetW& cn, const bf16* image8, i
   c.ws->release(m);
 }
 
-// ControlNet (control_net.py:45-107): writes 13 dense bf16 residual tensors into res[i].
+// ControlNet (control_net.py:45-107): writes 13 dense bf16 residual tensors into res[i] — or, with `into` (the UNet's 12
+// skip tensors and its middle-block output, from unet_encode), ADDS them there: the zero-convolution's epilogue reads its
+// output tile as the residual and stores the sum in place (diffusion_model.py:230-234 without a separate add).
 inline void controlnet_forward(Ctx& c, const ControlNetW& cn, const bf16* latent8, int B, int h, int w, const float* t_emb,
-                               const CtxKV& kv, const View& hint, View* res /*[13]*/, const float* time_tab = nullptr) {
+                               const CtxKV& kv, const View& hint, View* res /*[13]*/, const float* time_tab = nullptr,
+                               const UNetState* into = nullptr) {
   const size_t m0 = c.ws->mark();
   const float* tab = time_tab ? time_tab : time_table(c, cn.enc.time, t_emb, B);
   const int tl = cn.enc.time.ncat;
@@ -502,56 +533,30 @@ inline void controlnet_forward(Ctx& c, const ControlNetW& cn, const bf16* latent
   lat.p = const_cast<bf16*>(latent8); lat.B = B; lat.H = h; lat.W = w; lat.C = 8; lat.ld = 8;
   c.conv(lat, cn.enc.conv_in, outs[0], 1, 1, &hint);  // conv_in(latent) + hint (control_net.py:56)
   encoder_half(c, cn.enc, outs, xmid, tab, tl, kv);
-  for (int k = 0; k < 12; ++k) c.conv(outs[k], cn.zero[k], res[k]);
-  c.conv(xmid, cn.zero[12], res[12]);
+  for (int k = 0; k < 13; ++k) {
+    const View& src = k < 12 ? outs[k] : xmid;
+    if (into) {
+      const View& dst = k < 12 ? into->outs[k] : into->xmid;
+      c.conv(src, cn.zero[k], dst, 1, -1, &dst);
+    } else {
+      c.conv(src, cn.zero[k], res[k]);
+    }
+  }
   c.ws->release(m0);
 }
 
-// VAE AttentionBlock (layers.py:28-59): single head, d = C = 512, scores materialised per sample through the
-// GEMM kernel (S = Q K^T scaled, row softmax, O = P V with V^T produced by a swapped-operand GEMM).
+// VAE AttentionBlock (layers.py:28-59): GroupNorm, one q | k | v GEMM, the single-head d = 512 flash kernel (attn.cuh
+// vattn_kernel: no N x N tensor), output projection + residual.
 inline void vae_attention(Ctx& c, const VaeAttnW& w, const View& x, const View& out) {
   const size_t m = c.ws->mark();
   const int B = x.B, N = x.H * x.W, C = x.C;
+  SDTF_CHECK(C == 512, "VAE attention block: 512 channels expected");
   View t = c.alloc_view(B, x.H, x.W, C);
   c.groupnorm(x, w.gn, false, t);
-  View q = c.alloc_view(B, x.H, x.W, C), k = c.alloc_view(B, x.H, x.W, C), o = c.alloc_view(B, x.H, x.W, C);
-  c.conv(t.tokens(), w.q, q.tokens());
-  c.conv(t.tokens(), w.k, k.tokens());
-  bf16* vT = c.ws->alloc_n<bf16>((size_t)C * N);
-  float* S = c.ws->alloc_n<float>((size_t)N * N);
-  bf16* P = c.ws->alloc_n<bf16>((size_t)N * N);
-  const float scale = 1.f / sqrtf((float)C);
-  for (int b = 0; b < B; ++b) {
-    // V^T[c][n] = sum_k Wv[c][k] * t_b[n][k]   (A = Wv as a 512-row "activation", B operand = the tokens)
-    PackedWeight tokw;
-    tokw.w = t.p + (size_t)b * N * C; tokw.K = C; tokw.N = N;
-    View wv;
-    wv.p = w.v.w; wv.B = 1; wv.H = 1; wv.W = C; wv.C = C; wv.ld = C;
-    ConvArgs a1;
-    a1.a0 = wv; a1.w = &tokw; a1.outH = 1; a1.outW = C; a1.out = vT; a1.out_ld = N;
-    c.conv(a1);
-    // S = (Q K^T) / sqrt(C)
-    PackedWeight kw;
-    kw.w = k.p + (size_t)b * N * C; kw.K = C; kw.N = N;
-    View qb;
-    qb.p = q.p + (size_t)b * N * C; qb.B = 1; qb.H = 1; qb.W = N; qb.C = C; qb.ld = C;
-    ConvArgs a2;
-    a2.a0 = qb; a2.w = &kw; a2.outH = 1; a2.outW = N; a2.out = S; a2.out_ld = N; a2.out_fp32 = true; a2.out_scale = scale;
-    c.conv(a2);
-    ++c.launches;
-    if (!c.dry) {
-      softmax_rows_kernel<<<(unsigned)N, 256, 0, c.st>>>(S, N, N, P, N);
-      SDTF_CUDA(cudaGetLastError());
-    }
-    // O = P V + b_v
-    PackedWeight vw;
-    vw.w = vT; vw.K = N; vw.N = C; vw.bias = w.v_bias;
-    View pv;
-    pv.p = P; pv.B = 1; pv.H = 1; pv.W = N; pv.C = N; pv.ld = N;
-    ConvArgs a3;
-    a3.a0 = pv; a3.w = &vw; a3.outH = 1; a3.outW = N; a3.out = o.p + (size_t)b * N * C; a3.out_ld = C;
-    c.conv(a3);
-  }
+  View qkv = c.alloc_view(B, x.H, x.W, 3 * C);
+  c.conv(t.tokens(), w.qkv, qkv.tokens());
+  View o = t;  // the normalised input is dead once q | k | v exist
+  c.vattn(qkv, N, w.v_bias, o);
   View xt = x.tokens();
   c.conv(o.tokens(), w.proj, out.tokens(), 1, -1, &xt);
   c.ws->release(m);

@@ -448,34 +448,6 @@ inline void launch_layernorm(cudaStream_t st, const bf16* x, long long ld, int C
 }
 
 // ------------------------------------------------------------------------------------------------------
-// row softmax fp32 -> bf16 (VAE mid-block attention, layers.py:48-50), one CTA per row
-// ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-softmax_rows_kernel(const float* __restrict__ s, long long lds, int n, bf16* __restrict__ p, long long ldp) {
-  const long long row = blockIdx.x;
-  const float* sr = s + row * lds;
-  __shared__ float red[8];
-  float mx = -INFINITY;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, sr[i]);
-  mx = warp_max(mx);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
-  __syncthreads();
-  mx = red[0];
-  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
-  __syncthreads();
-  float sum = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) sum += __expf(sr[i] - mx);
-  sum = warp_sum(sum);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
-  __syncthreads();
-  sum = 0.f;
-  for (int i = 0; i < 8; ++i) sum += red[i];
-  const float inv = 1.f / sum;
-  bf16* pr = p + row * ldp;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) pr[i] = __float2bfloat16(__expf(sr[i] - mx) * inv);
-}
-
-// ------------------------------------------------------------------------------------------------------
 // skinny linear for the time-embedding chain (diffusion_model.py:184-188 and every ResBlock's
 // time_emb_proj :30,47): out[m][n] = act(sum_k x[m][k] * W[n][k] + b[n]), M <= 64 rows, one warp per n.
 // ------------------------------------------------------------------------------------------------------

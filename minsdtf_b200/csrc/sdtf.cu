@@ -734,13 +734,7 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
     float* d_initl = inpaint ? c.ws->alloc_n<float>((size_t)n) : nullptr;
     float* d_initn = inpaint ? c.ws->alloc_n<float>((size_t)B * n) : nullptr;
     View hint;
-    View ctrl[13];
-    static const int lv[13] = {0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 3, 3};
-    static const int ch[13] = {320, 320, 320, 320, 640, 640, 640, 1280, 1280, 1280, 1280, 1280, 1280};
-    if (control) {
-      hint = c.alloc_view(Bt, h, w, 320);
-      for (int i = 0; i < 13; ++i) ctrl[i] = c.alloc_view(Bt, h >> lv[i], w >> lv[i], ch[i]);
-    }
+    if (control) hint = c.alloc_view(Bt, h, w, 320);
     auto copy_in = [&](void* dst, const TRef& t) {
       if (!c.dry) SDTF_CUDA(cudaMemcpyAsync(dst, t.data, t.bytes(), t.cuda ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, e->st));
     };
@@ -816,12 +810,12 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
         }
       }
       for (Pass& ps : passes) {
-        const bf16* cptr[13];
-        if (control) {
-          controlnet_forward(sc, e->cnet, lat8, Bt, h, w, nullptr, ps.kv_cn, hint, ctrl, tab_c);
-          for (int i = 0; i < 13; ++i) cptr[i] = ctrl[i].p;
-        }
-        unet_forward(sc, e->unet, lat8, Bt, h, w, nullptr, ps.kv, control ? cptr : nullptr, eps + ps.eps_off, tab_u);
+        // UNet encoder half, then ControlNet (its zero-convolutions add into the UNet's skip tensors from their own
+        // epilogue, diffusion_model.py:230-234), then the UNet's up path
+        UNetState us;
+        unet_encode(sc, e->unet, lat8, Bt, h, w, nullptr, ps.kv, tab_u, us);
+        if (control) controlnet_forward(sc, e->cnet, lat8, Bt, h, w, nullptr, ps.kv_cn, hint, nullptr, tab_c, &us);
+        unet_decode(sc, e->unet, Bt, h, w, ps.kv, us, eps + ps.eps_off);
       }
       if (split) {  // C1: in-place all-gather of this rank's branch; both ranks then run the update redundantly
         ++sc.launches;
@@ -1095,6 +1089,26 @@ int sdtf_test_attention(sdtf_engine* e, const DLManagedTensor* q_t, const DLMana
   expect_shape(k, {B, Nk, C}, "k");
   expect_shape(v, {B, Nk, C}, "v");
   expect_shape(out, {B, Nq, C}, "out");
+  if (heads == 1 && d == 512) {  // the VAE mid-block attention kernel: one head of 512, q | k | v interleaved per token
+    SDTF_CHECK(Nq == Nk, "the d = 512 kernel is self-attention");
+    e->run_sized([&](Ctx& c) {
+      View qkv = c.alloc_view(B, 1, Nq, 3 * C), o = c.alloc_view(B, 1, Nq, C);
+      const TRef* src[3] = {&q, &k, &v};
+      for (int i = 0; i < 3; ++i) {
+        float* f = e->stage_f32(c, *src[i]);
+        View part = c.alloc_view(B, 1, Nq, C);
+        c.cast_pad(f, (long long)B * Nq, C, C, 1.f, part.p, false);
+        if (!c.dry) SDTF_CUDA(cudaMemcpy2DAsync(qkv.p + (size_t)i * C, (size_t)3 * C * 2, part.p, (size_t)C * 2, (size_t)C * 2,
+                                                 (size_t)B * Nq, cudaMemcpyDeviceToDevice, e->st));
+      }
+      c.vattn(qkv, Nq, nullptr, o);
+      float* fo = c.ws->alloc_n<float>((size_t)B * Nq * C);
+      c.cast_out(o.p, C, (long long)B * Nq, C, fo);
+      e->emit(c, fo, out);
+    });
+    SDTF_CUDA(cudaStreamSynchronize(e->st));
+    return SDTF_OK;
+  }
   e->run_sized([&](Ctx& c) {
     float* fq = e->stage_f32(c, q);
     float* fk = e->stage_f32(c, k);

@@ -58,6 +58,12 @@ def test_attention_d40_kernels_agree(engine, B, Nq, Nk, heads, d):
     _check_attention(engine, B, Nq, Nk, heads, d, legacy=False)
 
 
+@pytest.mark.parametrize("B,N", [(2, 256), (1, 320), (1, 64), (1, 4096), (1, 9216)])
+def test_vae_attention_flash_kernel_matches_torch(engine, B, N):
+    """single head of 512 (layers.py:28-59): 16x16 / ragged 20x16 / 8x8 latents, 64x64 (512x512 images), 96x96 (768x768)"""
+    _check_attention(engine, B, N, N, 1, 512, legacy=False)
+
+
 def _check_attention(engine, B, Nq, Nk, heads, d, legacy):
     g = torch.Generator().manual_seed(B * 1000 + Nq + Nk + d)
     C = heads * d
