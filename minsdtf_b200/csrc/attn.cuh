@@ -9,8 +9,9 @@
 //   O (+)= P V       tcgen05.mma  M=128, N=d, K=keys; V is read straight from its [key][d] layout as an
 //                    MN-major B operand, O accumulates in TMEM columns [128, 128+d) and is rescaled in
 //                    place (tcgen05.ld / st) when the running max moves.
-// Q/K/V tiles arrive by TMA (3-D maps: column, token, batch) so ragged key counts (77-token context)
-// are zero-filled by the hardware and masked in the softmax.
+// Q/K/V tiles arrive by TMA through 4-D maps (column within the head, head, token, batch): a head's 64-column box is
+// clipped at the head size d by the hardware (d = 40: columns 40..63 of the shared-memory row are zero-filled, nothing
+// is padded in HBM), and ragged key counts (77-token context) are zero-filled the same way and masked in the softmax.
 #pragma once
 #include "common.cuh"
 #include "tc05.cuh"
@@ -20,7 +21,7 @@ namespace sdtf {
 struct AttnParams {
   int Nq, Nk;        // queries / keys per batch element
   int d;             // true head size (scale = d^-1/2, output columns per head)
-  int dstride;       // column distance between heads in the Q/K/V matrices (64 for d=40: zero padded)
+  int dstride;       // column distance between heads in the Q/K/V matrices (= d: heads are stored densely)
   float scale_log2;  // d^-1/2 * log2(e)
   bf16* out;         // [B*Nq][ldo], head h at column h*d
   long long ldo;
@@ -60,7 +61,6 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
-  const int col0 = head * p.dstride;
   const int nkv = (p.Nk + 127) / 128;
   const bool leader = threadIdx.x == 0;
 
@@ -83,12 +83,12 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
   auto load_k = [&](int j) {
     const int st = j % KST;
     mbar_expect_tx(k_full(st), DCH * kChunk);
-    for (int c = 0; c < DCH; ++c) tma_load_3d(sK + (st * DCH + c) * kChunk, &tmK, k_full(st), col0 + 64 * c, j * 128, b);
+    for (int c = 0; c < DCH; ++c) tma_load_4d(sK + (st * DCH + c) * kChunk, &tmK, k_full(st), 64 * c, head, j * 128, b);
   };
   auto load_v = [&](int j) {
     const int st = j % VST;
     mbar_expect_tx(v_full(st), DCH * kChunk);
-    for (int c = 0; c < DCH; ++c) tma_load_3d(sV + (st * DCH + c) * kChunk, &tmV, v_full(st), col0 + 64 * c, j * 128, b);
+    for (int c = 0; c < DCH; ++c) tma_load_4d(sV + (st * DCH + c) * kChunk, &tmV, v_full(st), 64 * c, head, j * 128, b);
   };
   auto keys_in_tile = [&](int j) {  // valid keys of tile j rounded up to the MMA granularity
     int n = p.Nk - j * 128;
@@ -111,7 +111,7 @@ attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUt
 
   if (leader) {
     mbar_expect_tx(q_full, DCH * kChunk);
-    for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + c * kChunk, &tmQ, q_full, col0 + 64 * c, q0, b);
+    for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + c * kChunk, &tmQ, q_full, 64 * c, head, q0, b);
     for (int j = 0; j < KST && j < nkv; ++j) load_k(j);
     for (int j = 0; j < VST && j < nkv; ++j) load_v(j);
     mbar_wait(q_full, 0);
@@ -355,7 +355,6 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
-  const int col0 = head * p.dstride;
   const int nkv = (p.Nk + 127) / 128;
   const bool prof_on = p.prof != nullptr;
   const long long t_start = prof_on ? clock64() : 0;
@@ -389,8 +388,8 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_expect_tx(q_full, 2 * DCH * kChunk);
 #pragma unroll
       for (int c = 0; c < DCH; ++c) {
-        tma_load_3d(sQ + c * kChunk, &tmQ, q_full, col0 + 64 * c, q0, b);
-        tma_load_3d(sQ + (DCH + c) * kChunk, &tmQ, q_full, col0 + 64 * c, q0 + 128, b);
+        tma_load_4d(sQ + c * kChunk, &tmQ, q_full, 64 * c, head, q0, b);
+        tma_load_4d(sQ + (DCH + c) * kChunk, &tmQ, q_full, 64 * c, head, q0 + 128, b);
       }
       long long w_ke = 0, w_ve = 0;
       for (int j = 0; j < nkv; ++j) {
@@ -400,14 +399,14 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         else {
           mbar_expect_tx(k_full(ks), DCH * kChunk);
 #pragma unroll
-          for (int c = 0; c < DCH; ++c) tma_load_3d(sK + (ks * DCH + c) * kChunk, &tmK, k_full(ks), col0 + 64 * c, j * 128, b);
+          for (int c = 0; c < DCH; ++c) tma_load_4d(sK + (ks * DCH + c) * kChunk, &tmK, k_full(ks), 64 * c, head, j * 128, b);
         }
         A2_TIMED(w_ve, mbar_wait(v_empty(vs), ((uint32_t)(j / VST) & 1u) ^ 1u));
         if (p.debug & 64) mbar_arrive(v_full(vs));
         else {
           mbar_expect_tx(v_full(vs), DCH * kChunk);
 #pragma unroll
-          for (int c = 0; c < DCH; ++c) tma_load_3d(sV + (vs * DCH + c) * kChunk, &tmV, v_full(vs), col0 + 64 * c, j * 128, b);
+          for (int c = 0; c < DCH; ++c) tma_load_4d(sV + (vs * DCH + c) * kChunk, &tmV, v_full(vs), 64 * c, head, j * 128, b);
         }
       }
       if (prof_on) {
@@ -661,7 +660,6 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
-  const int col0 = head * p.dstride;
   const int nkv = (p.Nk + 127) / 128;
 
   pdl_trigger();
@@ -698,16 +696,16 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // ===== TMA producer =====
     if (elect_one()) {
       mbar_expect_tx(q_full, 2 * kChunk);
-      tma_load_3d(sQ, &tmQ, q_full, col0, q0, b);
-      tma_load_3d(sQ + kChunk, &tmQ, q_full, col0, q0 + 128, b);
+      tma_load_4d(sQ, &tmQ, q_full, 0, head, q0, b);
+      tma_load_4d(sQ + kChunk, &tmQ, q_full, 0, head, q0 + 128, b);
       for (int j = 0; j < nkv; ++j) {
         const int ks = j % KST, vs = j % VST;
         mbar_wait(k_empty(ks), ((uint32_t)(j / KST) & 1u) ^ 1u);
         mbar_expect_tx(k_full(ks), kChunk);
-        tma_load_3d(sK + ks * kChunk, &tmK, k_full(ks), col0, j * 128, b);
+        tma_load_4d(sK + ks * kChunk, &tmK, k_full(ks), 0, head, j * 128, b);
         mbar_wait(v_empty(vs), ((uint32_t)(j / VST) & 1u) ^ 1u);
         mbar_expect_tx(v_full(vs), kChunk);
-        tma_load_3d(sV + vs * kChunk, &tmV, v_full(vs), col0, j * 128, b);
+        tma_load_4d(sV + vs * kChunk, &tmV, v_full(vs), 0, head, j * 128, b);
       }
     }
     __syncwarp();
@@ -1007,8 +1005,12 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.x, b = blockIdx.y;
-  const int col0 = head * p.dstride;
-  const int nqt = (p.Nq + 127) / 128;
+  // blockIdx.z splits the head's query tiles over several CTAs when (heads x batch) alone would leave most SMs idle
+  // (UNet batch 2: 16 CTAs); each CTA loads K / V for itself (a few KB)
+  const int nqt_all = (p.Nq + 127) / 128;
+  const int per_cta = (nqt_all + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int t0 = (int)blockIdx.z * per_cta;
+  const int nqt = max(0, min(nqt_all, t0 + per_cta) - t0);
   const int ncols = (p.Nk + 15) & ~15;  // keys rounded up to the MMA granularity (TMA zero-fills the missing rows)
 
   pdl_trigger();
@@ -1035,15 +1037,15 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       mbar_expect_tx(kv_full, 2 * DCH * kChunk);
 #pragma unroll
       for (int c = 0; c < DCH; ++c) {
-        tma_load_3d(sK + c * kChunk, &tmK, kv_full, col0 + 64 * c, 0, b);
-        tma_load_3d(sV + c * kChunk, &tmV, kv_full, col0 + 64 * c, 0, b);
+        tma_load_4d(sK + c * kChunk, &tmK, kv_full, 64 * c, head, 0, b);
+        tma_load_4d(sV + c * kChunk, &tmV, kv_full, 64 * c, head, 0, b);
       }
       for (int t = 0; t < nqt; ++t) {
         const int st = t % QST;
         if (t >= QST) mbar_wait(q_empty(st), (uint32_t)(t / QST - 1) & 1u);
         mbar_expect_tx(q_full(st), DCH * kChunk);
 #pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_3d(sQ + (st * DCH + c) * kChunk, &tmQ, q_full(st), col0 + 64 * c, t * 128, b);
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sQ + (st * DCH + c) * kChunk, &tmQ, q_full(st), 64 * c, head, (t0 + t) * 128, b);
       }
     }
     __syncwarp();
@@ -1155,7 +1157,7 @@ xattn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CU
       }
       tmem_ld_wait();
       fence_before_sync();
-      const int q = t * 128 + row;
+      const int q = (t0 + t) * 128 + row;
       if (q < p.Nq) {
         bf16* orow = p.out + ((long long)b * p.Nq + q) * p.ldo + head * p.d;
 #pragma unroll
@@ -1463,12 +1465,13 @@ struct AttnArgs {
   bool legacy = false;  // force the one-tile-per-CTA kernel (A/B measurements)
 };
 
-inline CUtensorMap make_tok_tmap(const bf16* base, int cols, int N, int B, long long ld) {
-  uint64_t dims[3] = {(uint64_t)cols, (uint64_t)N, (uint64_t)B};
-  uint64_t strides[2] = {(uint64_t)ld * 2, (uint64_t)N * ld * 2};
-  uint32_t box[3] = {64, 128, 1};
-  uint32_t es[3] = {1, 1, 1};
-  return make_tmap_bf16(base, 3, dims, strides, box, es);
+// (column within head, head, token, batch); box = 64 columns x 1 head x 128 tokens: columns past d are zero-filled
+inline CUtensorMap make_tok_tmap(const bf16* base, int d, int dstride, int heads, int N, int B, long long ld) {
+  uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)N, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)dstride * 2, (uint64_t)ld * 2, (uint64_t)N * ld * 2};
+  uint32_t box[4] = {64, 1, 128, 1};
+  uint32_t es[4] = {1, 1, 1, 1};
+  return make_tmap_bf16(base, 4, dims, strides, box, es);
 }
 
 template <int DCH, int KS, int DV, int KST, int VST>
@@ -1524,27 +1527,27 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
     SDTF_CUDA(cudaMemsetAsync(prof_buf, 0, 16 * sizeof(long long), stream));
     p.prof = prof_buf;
   }
-  const int cols = a.heads * a.dstride;
-  CUtensorMap tq = make_tok_tmap(a.q, cols, a.Nq, a.B, a.ldq);
-  CUtensorMap tk = make_tok_tmap(a.k, cols, a.Nk, a.B, a.ldk);
-  CUtensorMap tv = make_tok_tmap(a.v, cols, a.Nk, a.B, a.ldv);
+  SDTF_CHECK(a.dstride % 8 == 0, "attention: heads must start on 16-byte boundaries");
+  CUtensorMap tq = make_tok_tmap(a.q, a.d, a.dstride, a.heads, a.Nq, a.B, a.ldq);
+  CUtensorMap tk = make_tok_tmap(a.k, a.d, a.dstride, a.heads, a.Nk, a.B, a.ldk);
+  CUtensorMap tv = make_tok_tmap(a.v, a.d, a.dstride, a.heads, a.Nk, a.B, a.ldv);
   // short contexts (the 77-token prompt): one CTA per (sample, head), K / V resident, query tiles pipelined
   static const int use_xattn = getenv("SDTF_XATTN") ? atoi(getenv("SDTF_XATTN")) : 1;
   if (use_xattn && !a.legacy && a.Nk <= 128 && a.Nq >= 256 && (a.d == 40 || a.d == 80)) {
-    dim3 grid((unsigned)a.heads, (unsigned)a.B);
+    const int nqt = ceil_div(a.Nq, 128), hb = a.heads * a.B;
+    int zsplit = hb >= 96 ? 1 : (148 + hb - 1) / hb;  // fill the machine when (heads x batch) is small
+    if (zsplit > nqt) zsplit = nqt;
+    dim3 grid((unsigned)a.heads, (unsigned)a.B, (unsigned)zsplit);
     if (a.d == 40) {
-      SDTF_CHECK(a.dstride == 64, "d=40 heads must be stored zero-padded to 64 columns");
       if (a.Nk <= 80) launch_pdl(xattn_kernel<1, 3, 48, 4, 80>, grid, dim3(kXAThreads), xattn_smem_bytes<1, 4>(), stream, 1, tq, tk, tv, p);
       else launch_pdl(xattn_kernel<1, 3, 48, 4, 128>, grid, dim3(kXAThreads), xattn_smem_bytes<1, 4>(), stream, 1, tq, tk, tv, p);
     } else {
-      SDTF_CHECK(a.dstride == 80, "d=80 heads are stored densely");
       if (a.Nk <= 80) launch_pdl(xattn_kernel<2, 5, 80, 3, 80>, grid, dim3(kXAThreads), xattn_smem_bytes<2, 3>(), stream, 1, tq, tk, tv, p);
       else launch_pdl(xattn_kernel<2, 5, 80, 3, 128>, grid, dim3(kXAThreads), xattn_smem_bytes<2, 3>(), stream, 1, tq, tk, tv, p);
     }
     return;
   }
   if (a.d == 40) {
-    SDTF_CHECK(a.dstride == 64, "d=40 heads must be stored zero-padded to 64 columns");
     if (a.legacy) {
       launch_attn_t<1, 3, 48, 2, 2>(stream, a, p, tq, tk, tv);
     } else {
@@ -1580,7 +1583,6 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
       }
     }
   } else if (a.d == 80) {
-    SDTF_CHECK(a.dstride == 80, "d=80 heads are stored densely");
     if (a.legacy) {
       launch_attn_t<2, 5, 80, 2, 2>(stream, a, p, tq, tk, tv);
     } else {  // two query tiles per CTA, warp-specialised (softmax of one tile overlaps the MMAs of the other)
@@ -1588,7 +1590,6 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
       launch_pdl(attn2q_kernel<2, 5, 80, 2, 1>, grid, dim3(kA2Threads), attn2q_smem_bytes<2, 2, 1>(), stream, 1, tq, tk, tv, p);
     }
   } else if (a.d == 160) {
-    SDTF_CHECK(a.dstride == 160, "d=160 heads are stored densely");
     launch_attn_t<3, 10, 160, 1, 1>(stream, a, p, tq, tk, tv);
   } else {
     throw Error("attention: unsupported head size " + std::to_string(a.d));

@@ -120,6 +120,19 @@ inline CUtensorMap make_epi_tmap(const bf16* base, int C, int W, int H, int B, l
   return make_tmap_bf16(base, 4, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_64B);
 }
 
+// epilogue map over an output whose columns are HEADS of `head_stride` columns of which only the first `d` are real
+// (q | k | v of the d = 40 attention levels: heads sit 64 columns apart so that a head is one aligned 128-byte row for
+// the attention kernel's TMA loads, but the 24 padding columns are never written — the store is clipped at d by the
+// hardware — and never read: the load maps clip too).  dims (d, heads, W, H, B); box (32, 1, bw, bh, bn).
+inline CUtensorMap make_epi_tmap_heads(const bf16* base, int d, int head_stride, int heads, int W, int H, int B, long long ld, int bw,
+                                       int bh, int bn) {
+  uint64_t dims[5] = {(uint64_t)d, (uint64_t)heads, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[4] = {(uint64_t)head_stride * 2, (uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+  uint32_t box[5] = {32, 1, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+  uint32_t es[5] = {1, 1, 1, 1, 1};
+  return make_tmap_bf16(base, 5, dims, strides, box, es, CU_TENSOR_MAP_SWIZZLE_64B);
+}
+
 // packed weight map [taps][N][K]: dims (K, N, taps), box (64, BN, 1)
 inline CUtensorMap make_weight_tmap(const bf16* w, int K, int N, int taps, int BN) {
   uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, (uint64_t)taps};

@@ -137,6 +137,7 @@ struct Ctx {
   bool dry = false;
   int launches = 0;
   GnScratch gn;
+  int batch_class = 0;  // samples per denoise step (both CFG branches) when calls see one branch at a time; 0: the call's own batch
 
   template <class F>
   void traced(const char* kind, const std::string& shape, double flop, double bytes, F&& f) {
@@ -191,6 +192,7 @@ struct Ctx {
     ++launches;
     // split-K scratch (fp32 partial sums) lives in the arena for the duration of the launch pair
     ConvArgs a = a0;
+    if (!a.batch_class) a.batch_class = batch_class;
     const size_t sk_floats = a.splitk_ws ? 0 : conv_splitk_floats(a);
     const size_t sk_mark = ws->mark();
     if (sk_floats) {
@@ -209,11 +211,27 @@ struct Ctx {
     traced("conv", buf, 2.0 * M * w.N * K * w.kh * w.kw,
            2.0 * ((double)a.a0.B * a.a0.H * a.a0.W * K + M * Nout * (a.res ? 2 : 1) + (double)w.N * K * w.kh * w.kw),
            [&] { launch_conv(st, a); });
-    if (!a.out_fp32 && a.out_step == 1) fingerprint("conv", reinterpret_cast<const bf16*>(a.out), a.out_ld, Nout, (long long)a.outH * a.outW, a.a0.B);
+    if (!a.out_fp32 && a.out_step == 1 && a.out_head_stride == 0) fingerprint("conv", reinterpret_cast<const bf16*>(a.out), a.out_ld, Nout, (long long)a.outH * a.outW, a.a0.B);
   }
   // y = conv(x) (+bias) (+temb) (+res) ; out view may be a channel slice
+  // linear whose output columns are attention heads stored `head_stride` columns apart (d real columns each): the
+  // padding columns are neither computed-and-written nor read (clipped TMA store / loads)
+  static ConvArgs args_heads(const View& x, const PackedWeight& w, const View& out, int d, int head_stride) {
+    ConvArgs a;
+    a.a0 = x; a.w = &w;
+    a.outH = out.H; a.outW = out.W;
+    a.out = out.p; a.out_ld = out.ld;
+    static const int clip = getenv("SDTF_HEAD_CLIP") ? atoi(getenv("SDTF_HEAD_CLIP")) : 1;  // A/B: 0 = write the (zero) padding columns too
+    if (head_stride != d && clip) { a.out_head_d = d; a.out_head_stride = head_stride; }
+    return a;
+  }
+  void conv_heads(const View& x, const PackedWeight& w, const View& out, int d, int head_stride) { conv(args_heads(x, w, out, d, head_stride)); }
   void conv(const View& x, const PackedWeight& w, const View& out, int stride = 1, int pad = -1, const View* res = nullptr,
             const float* temb = nullptr, int temb_ld = 0, int act = ACT_NONE, const View* x2 = nullptr) {
+    conv(args(x, w, out, stride, pad, res, temb, temb_ld, act, x2));
+  }
+  static ConvArgs args(const View& x, const PackedWeight& w, const View& out, int stride = 1, int pad = -1, const View* res = nullptr,
+                       const float* temb = nullptr, int temb_ld = 0, int act = ACT_NONE, const View* x2 = nullptr) {
     ConvArgs a;
     a.a0 = x;
     if (x2) a.a1 = *x2;
@@ -226,7 +244,7 @@ struct Ctx {
     if (res) { a.res = res->p; a.res_ld = res->ld; }
     a.out = out.p; a.out_ld = out.ld;
     a.act = act;
-    conv(a);
+    return a;
   }
   // y = conv3x3(upsample2x(x)) without the upsampled tensor: one 2x2 conv per output parity, each writing every other
   // pixel of y through a strided TMA store map
@@ -249,7 +267,7 @@ struct Ctx {
     if (dry || (skip_mask() & SKIP_GN)) return;
     char buf[64];
     snprintf(buf, sizeof buf, "%dx%dx%dx%d%s", x.B, x.H, x.W, x.C, silu ? " silu" : "");
-    traced("gn", buf, 0.0, 4.0 * x.pixels() * x.C, [&] { launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn); });
+    traced("gn", buf, 0.0, 4.0 * x.pixels() * x.C, [&] { launch_groupnorm(st, x, n.gamma, n.beta, silu, y.p, y.ld, gn, batch_class); });
     fingerprint("gn", y.p, y.ld, x.C, (long long)x.H * x.W, x.B);
   }
   void layernorm(const View& x, const NormW& n, const View& y) {
@@ -343,7 +361,10 @@ struct WeightStore {
   void free_map(int* d) { SDTF_CUDA(cudaFreeAsync(d, st)); }
 
   // pack rows of `key` ([O][I][kh][kw] or [O][I]) into dst [taps][Ntot][Kp] at row n0, column k0
-  void pack_into(bf16* dst, int Ntot, int Kp, int n0, int k0, const RawTensor& t, const std::vector<int>* row_map, float scale) {
+  // `ln` (optional): a LayerNorm over the I input columns is folded in — gamma scales the columns here, and the per-row
+  // constants c1 / c0 (ops.cuh ln_fold_consts_kernel) are written to ln_c1 / accumulated into ln_c0 at rows n0 + [0, nrows)
+  void pack_into(bf16* dst, int Ntot, int Kp, int n0, int k0, const RawTensor& t, const std::vector<int>* row_map, float scale,
+                 const NormW* ln = nullptr, float* ln_c1 = nullptr, float* ln_c0 = nullptr) {
     const int O = (int)t.shape[0], I = (int)t.shape[1];
     const int taps = t.shape.size() == 4 ? (int)(t.shape[2] * t.shape[3]) : 1;
     const int nrows = row_map ? (int)row_map->size() : O;
@@ -352,9 +373,19 @@ struct WeightStore {
     long long blocks = ceil_div_ll(total, 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
     if (blocks < 1) blocks = 1;
-    pack_weight_kernel<<<(unsigned)blocks, 256, 0, st>>>(t.p, I, taps, dm, nrows, n0, Ntot, Kp, k0, scale, dst);
+    pack_weight_kernel<<<(unsigned)blocks, 256, 0, st>>>(t.p, I, taps, dm, nrows, n0, Ntot, Kp, k0, scale, dst, ln ? ln->gamma : nullptr);
     SDTF_CUDA(cudaGetLastError());
+    if (ln) {
+      SDTF_CHECK(taps == 1 && k0 == 0 && scale == 1.f && ln->C == I && ln_c1 && ln_c0, "LayerNorm folding: plain linear over the normalised axis only");
+      ln_fold_consts_kernel<<<ceil_div(nrows, 8), 256, 0, st>>>(t.p, I, dm, nrows, n0, ln->gamma, ln->beta, ln_c1, ln_c0);
+      SDTF_CUDA(cudaGetLastError());
+    }
     if (dm) free_map(dm);
+  }
+  float* zeros_f32(int n) {
+    float* p = (float*)pool.alloc((size_t)n * 4);
+    SDTF_CUDA(cudaMemsetAsync(p, 0, (size_t)n * 4, st));
+    return p;
   }
   float* pack_vec(const RawTensor& t, const std::vector<int>* row_map, float scale, float* dst = nullptr, int n0 = 0) {
     const int n = row_map ? (int)row_map->size() : (int)t.numel();
@@ -367,7 +398,9 @@ struct WeightStore {
   }
 
   // plain conv / linear: key.weight [+ key.bias]
-  PackedWeight conv(const std::string& key, bool bias = true, float scale = 1.f, const std::vector<int>* row_map = nullptr) {
+  // `ln`: fold the LayerNorm that precedes this linear into it (gemm.cuh GemmParams::ln_in)
+  PackedWeight conv(const std::string& key, bool bias = true, float scale = 1.f, const std::vector<int>* row_map = nullptr,
+                    const NormW* ln = nullptr) {
     PackedWeight pw;
     const RawTensor* w = find(key + ".weight");
     const RawTensor* b = bias ? find(key + ".bias") : nullptr;
@@ -380,8 +413,15 @@ struct WeightStore {
     const size_t n = (size_t)pw.kh * pw.kw * pw.N * pw.K;
     pw.w = (bf16*)pool.alloc(n * 2);
     SDTF_CUDA(cudaMemsetAsync(pw.w, 0, n * 2, st));
-    pack_into(pw.w, pw.N, pw.K, 0, 0, *w, row_map, scale);
     if (b) pw.bias = pack_vec(*b, row_map, scale);
+    if (ln && ln->gamma) {
+      if (!pw.bias) pw.bias = zeros_f32(pw.N);
+      pw.ln_c1 = zeros_f32(pw.N);
+      pw.ln_channels = I;
+      pack_into(pw.w, pw.N, pw.K, 0, 0, *w, row_map, scale, ln, pw.ln_c1, pw.bias);
+    } else {
+      pack_into(pw.w, pw.N, pw.K, 0, 0, *w, row_map, scale);
+    }
     return pw;
   }
   UpConvW upconv(const std::string& key) {
@@ -414,7 +454,7 @@ struct WeightStore {
     return n;
   }
   // several [O_i][I] matrices stacked along N (q|k|v, k|v); heads optionally zero-padded from d to dpad rows
-  PackedWeight stack(const std::vector<std::string>& keys, int heads, int d, int dpad) {
+  PackedWeight stack(const std::vector<std::string>& keys, int heads, int d, int dpad, const NormW* ln = nullptr) {
     PackedWeight pw;
     std::vector<const RawTensor*> ts;
     for (auto& k : keys) ts.push_back(find(k + ".weight"));
@@ -429,11 +469,18 @@ struct WeightStore {
     pw.K = (I + 7) / 8 * 8;
     pw.w = (bf16*)pool.alloc((size_t)pw.N * pw.K * 2);
     SDTF_CUDA(cudaMemsetAsync(pw.w, 0, (size_t)pw.N * pw.K * 2, st));
-    for (size_t i = 0; i < ts.size(); ++i) pack_into(pw.w, pw.N, pw.K, (int)i * per, 0, *ts[i], &map, 1.f);
+    if (ln && ln->gamma) {
+      pw.bias = zeros_f32(pw.N);
+      pw.ln_c1 = zeros_f32(pw.N);
+      pw.ln_channels = I;
+    } else {
+      ln = nullptr;
+    }
+    for (size_t i = 0; i < ts.size(); ++i) pack_into(pw.w, pw.N, pw.K, (int)i * per, 0, *ts[i], &map, 1.f, ln, pw.ln_c1, pw.bias);
     return pw;
   }
   // GEGLU projection [8C][C]: rows interleaved per 256-wide N tile as [128 value | 128 gate]
-  PackedWeight geglu(const std::string& key) {
+  PackedWeight geglu(const std::string& key, const NormW* ln = nullptr) {
     const RawTensor* w = find(key + ".weight");
     PackedWeight pw;
     if (!w) return pw;
@@ -444,7 +491,7 @@ struct WeightStore {
         map[t * 256 + j] = t * 128 + j;
         map[t * 256 + 128 + j] = half + t * 128 + j;
       }
-    pw = conv(key, true, 1.f, &map);
+    pw = conv(key, true, 1.f, &map, ln);
     pw.geglu_half = 128;
     return pw;
   }

@@ -49,6 +49,7 @@ struct Gemm3Extra {
   float* partial;        // split-K: fp32 partial sums [splits][B*H*W][N] (the reduce kernel applies the epilogue)
   long long* prof;       // optional [gridDim.x][16] cycle counters per role (null: off); see gemm_host.cuh
   int debug;             // timing experiments only (results are garbage): 1 = skip the MMA instructions, 2 = skip the TMA loads
+  int head_stride;       // > 0: output columns are heads of this many columns, tmOut is 5-D (make_epi_tmap_heads) and clips each head
 };
 
 // cycle accounting for the role loops (only when x.prof is set): t += clock spent inside a wait
@@ -297,7 +298,10 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const int buf = sg & nb_mask;
           // all 4 epilogue warps staged (and fenced) their rows
           G3_TIMED(prof_on, w_stg, mbar_wait(stg_bar(buf), (uint32_t)(sg >> nb_shift) & 1u));
-          tma_store_4d(&tmOut, smem_base + stg_off + (uint32_t)buf * kG3BufBytes, n_tile * ncols + pass_col(ps), x0, y0, b0);
+          const int col = n_tile * ncols + pass_col(ps);
+          const uint32_t src = smem_base + stg_off + (uint32_t)buf * kG3BufBytes;
+          if (x.head_stride) tma_store_5d(&tmOut, src, col % x.head_stride, col / x.head_stride, x0, y0, b0);
+          else tma_store_4d(&tmOut, src, col, x0, y0, b0);
           bulk_commit();
           if (sg >= 1) {
             // store sg-1 no longer reads its buffer: it can host pass sg-1+kG3Bufs
@@ -327,7 +331,9 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
     long long w_tfull = 0, w_grant = 0;
     const int et = (int)threadIdx.x - 128;  // 0..255 (set 0: 0..127)
-    const bool has_vec = p.bias != nullptr || p.temb != nullptr;
+    const bool has_vec = p.bias != nullptr || p.temb != nullptr || p.ln_c1 != nullptr;
+    const bool ln_apply = p.ln_in != nullptr;
+    const int rpb = 1 << x.log_rows_per_b;
     const int vrows = x.vec_rows, vwidth = x.vec_width;
     const int Nvec = geglu ? p.N : Nout;
     float* vec = reinterpret_cast<float*>(smem_gen + vec_off);
@@ -342,6 +348,27 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int ps_last = ps0 + ((passes - 1 - ps0) & ~1);  // last one (< ps0 if the set has none)
       int vr = row >> x.log_rows_per_b;  // sample of this row inside the tile
       vr = vr < vrows ? vr : vrows - 1;
+      if (ln_apply) vr = 0;              // LayerNorm consumer: vector row 0 = c0 (bias), row 1 = c1
+      // global pixel index of this thread's row (LayerNorm statistics are indexed by it)
+      long long ln_m = -1;
+      if (ln_apply || p.ln_out) {
+        const int rr = row & (rpb - 1);
+        const int pb = b0 + (row >> x.log_rows_per_b), py = y0 + rr / p.bw, px = x0 + rr % p.bw;
+        if (pb < p.B && py < p.H && px < p.W) ln_m = ((long long)pb * p.H + py) * p.W + px;
+      }
+      float ln_a = 1.f, ln_b = 0.f;
+      if (ln_apply && ln_m >= 0) {  // issued before the accumulator wait: the loads hide behind the main loop
+        float s1 = 0.f, s2 = 0.f;
+        for (int sl = 0; sl < p.ln_slots; ++sl) {
+          const float2 t2 = __ldg(p.ln_in + (long long)sl * p.ln_rows + ln_m);
+          s1 += t2.x; s2 += t2.y;
+        }
+        const float mean = s1 * p.ln_inv_c;
+        const float var = fmaxf(s2 * p.ln_inv_c - mean * mean, 0.f);
+        ln_a = rsqrtf(var + 1e-5f);
+        ln_b = -ln_a * mean;
+      }
+      float ln_s1 = 0.f, ln_s2 = 0.f;
       // this tile's per-column vector (bias, + the time-embedding row of each sample the tile spans): fetched from
       // global BEFORE waiting for the accumulator so the latency hides behind the main loop, then staged in smem
       float4 pre[4];
@@ -352,8 +379,9 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int r = 0; r < 4; ++r) {
           float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
           if (r < vrows && gcol < Nvec) {
-            if (p.bias) a = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
-            if (p.temb) {
+            if (ln_apply && r == 1) a = __ldg(reinterpret_cast<const float4*>(p.ln_c1 + gcol));
+            else if (p.bias) a = __ldg(reinterpret_cast<const float4*>(p.bias + gcol));
+            if (p.temb && !ln_apply) {
               int bb = b0 + r;
               bb = bb < p.B ? bb : p.B - 1;
               const float4 t4 = __ldg(reinterpret_cast<const float4*>(p.temb + (long long)bb * p.temb_ld + gcol));
@@ -433,20 +461,38 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               bv = *reinterpret_cast<const float4*>(vrow + tc + i);
               bg = *reinterpret_cast<const float4*>(vrow + ncols + tc + i);
             }
-            f[i] = (__uint_as_float(v[i]) + bv.x) * gelu_tanh_fast(__uint_as_float(gv[i]) + bg.x);
-            f[i + 1] = (__uint_as_float(v[i + 1]) + bv.y) * gelu_tanh_fast(__uint_as_float(gv[i + 1]) + bg.y);
-            f[i + 2] = (__uint_as_float(v[i + 2]) + bv.z) * gelu_tanh_fast(__uint_as_float(gv[i + 2]) + bg.z);
-            f[i + 3] = (__uint_as_float(v[i + 3]) + bv.w) * gelu_tanh_fast(__uint_as_float(gv[i + 3]) + bg.w);
+            if (ln_apply) {  // value / gate = rstd (acc - mean c1) + c0
+              const float4 cv = *reinterpret_cast<const float4*>(vrow + vwidth + tc + i);
+              const float4 cg = *reinterpret_cast<const float4*>(vrow + vwidth + ncols + tc + i);
+              bv.x = fmaf(ln_b, cv.x, bv.x); bv.y = fmaf(ln_b, cv.y, bv.y); bv.z = fmaf(ln_b, cv.z, bv.z); bv.w = fmaf(ln_b, cv.w, bv.w);
+              bg.x = fmaf(ln_b, cg.x, bg.x); bg.y = fmaf(ln_b, cg.y, bg.y); bg.z = fmaf(ln_b, cg.z, bg.z); bg.w = fmaf(ln_b, cg.w, bg.w);
+            }
+            f[i] = fmaf(ln_a, __uint_as_float(v[i]), bv.x) * gelu_tanh_fast(fmaf(ln_a, __uint_as_float(gv[i]), bg.x));
+            f[i + 1] = fmaf(ln_a, __uint_as_float(v[i + 1]), bv.y) * gelu_tanh_fast(fmaf(ln_a, __uint_as_float(gv[i + 1]), bg.y));
+            f[i + 2] = fmaf(ln_a, __uint_as_float(v[i + 2]), bv.z) * gelu_tanh_fast(fmaf(ln_a, __uint_as_float(gv[i + 2]), bg.z));
+            f[i + 3] = fmaf(ln_a, __uint_as_float(v[i + 3]), bv.w) * gelu_tanh_fast(fmaf(ln_a, __uint_as_float(gv[i + 3]), bg.w));
           }
         } else {
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.out_scale;
-          if (has_vec) {
+          if (ln_apply) {  // y = rstd (acc - mean c1[n]) + c0[n]
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 bv = *reinterpret_cast<const float4*>(vrow + tc + i);
-              f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+              const float4 c0v = *reinterpret_cast<const float4*>(vrow + tc + i);
+              const float4 c1v = *reinterpret_cast<const float4*>(vrow + vwidth + tc + i);
+              f[i] = fmaf(ln_a, __uint_as_float(v[i]), fmaf(ln_b, c1v.x, c0v.x));
+              f[i + 1] = fmaf(ln_a, __uint_as_float(v[i + 1]), fmaf(ln_b, c1v.y, c0v.y));
+              f[i + 2] = fmaf(ln_a, __uint_as_float(v[i + 2]), fmaf(ln_b, c1v.z, c0v.z));
+              f[i + 3] = fmaf(ln_a, __uint_as_float(v[i + 3]), fmaf(ln_b, c1v.w, c0v.w));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) * p.out_scale;
+            if (has_vec) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 bv = *reinterpret_cast<const float4*>(vrow + tc + i);
+                f[i] += bv.x; f[i + 1] += bv.y; f[i + 2] += bv.z; f[i + 3] += bv.w;
+              }
             }
           }
         }
@@ -489,10 +535,28 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           o.z = pack_bf16(f[8 * c + 4], f[8 * c + 5]);
           o.w = pack_bf16(f[8 * c + 6], f[8 * c + 7]);
           *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) = o;
+          if (p.ln_out) {  // statistics of what the consumer will read: the bf16-rounded values
+            const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&ow[i]);
+              const float a0 = __bfloat162float(h2.x), a1 = __bfloat162float(h2.y);
+              ln_s1 += a0 + a1;
+              ln_s2 = fmaf(a0, a0, fmaf(a1, a1, ln_s2));
+            }
+          }
         }
         fence_proxy_async_smem();  // staged row (generic proxy) -> visible to the TMA store (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(stg_bar(buf));
+      }
+      // LayerNorm producer: this thread's passes of the tile all have the parity of ps0 -> slot (n_tile, parity).  A tile
+      // whose passes of one parity do not exist (a single 32-column pass) still writes that slot, as zeros, from the set
+      // that drew the blank.  (The column grouping must not depend on which WARP SET handled a pass: that follows the
+      // CTA-local tile counter, hence the grid size, hence the batch.)
+      if (p.ln_out && ln_m >= 0) {
+        const int par = ps0 & 1;
+        p.ln_out[(long long)(2 * n_tile + par) * p.ln_rows + ln_m] = make_float2(ln_s1, ln_s2);
       }
     }
     if (prof_on && threadIdx.x == 128) { prof[8] = w_tfull; prof[9] = w_grant; prof[10] = clock64() - t_start; prof[11] = lt; }

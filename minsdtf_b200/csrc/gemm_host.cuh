@@ -14,6 +14,8 @@ namespace sdtf {
 struct PackedWeight {
   bf16* w = nullptr;
   float* bias = nullptr;  // may be null
+  float* ln_c1 = nullptr; // LayerNorm folded in: rows carry gamma, bias = c0, ln_c1[n] = sum_k of the packed row (WeightStore::fold_ln)
+  int ln_channels = 0;    // channels the folded LayerNorm normalises (= true K)
   int K = 0, N = 0, kh = 1, kw = 1;
   int geglu_half = 0;  // >0: rows are interleaved [value x half | gate x half] per N tile of 2*half
 };
@@ -31,6 +33,13 @@ struct ConvArgs {
   long long res_ld = 0;
   void* out = nullptr;
   long long out_ld = 0;
+  int out_head_d = 0, out_head_stride = 0;  // > 0: output columns are heads `out_head_stride` apart, only the first `out_head_d` are stored
+  // LayerNorm folded into the surrounding GEMMs (gemm.cuh GemmParams::ln_*)
+  float2* ln_out = nullptr;      // producer: per-row partial (sum, sum of squares) slots of the output, [slots][pixels]
+  int* ln_slots_out = nullptr;   //           number of slots this launch filled (2 per N tile)
+  const float2* ln_in = nullptr; // consumer: partials of its A operand's rows (weights must have been packed with fold_ln)
+  int ln_slots = 0;
+  int batch_class = 0;  // samples of the whole denoise step when this call only sees part of them (0: a0.B); see plan_splitk
   int out_step = 1;  // > 1: output pixel (y, x) of this launch is pixel (step y, step x) of the tensor at `out` (see upconv)
   bool out_fp32 = false;
   int act = ACT_NONE;
@@ -118,7 +127,7 @@ struct G3Plan {
 // one tap) costs max(tensor cycles = 2*BN, operand bytes / L2->SM delivery rate); measured delivery is ~50 B/clk/SM
 // with every SM pulling (ncu: 256x160 tiles keep the tensor pipe 50 % busy, 256x256 tiles 80 %).  Tiles wider than
 // 256 columns are two MMAs per k-step and a single-buffered accumulator: their epilogue is not hidden.
-inline G3Plan plan_gemm3(int N, long long m_tiles, int act, int force_bn, int iters) {
+inline G3Plan plan_gemm3(int N, long long m_tiles, int act, int force_bn, int iters, bool whole_passes = false) {
   G3Plan best;
   int cands[40], nc = 0;
   const bool geglu = act == ACT_GEGLU;
@@ -138,6 +147,7 @@ inline G3Plan plan_gemm3(int N, long long m_tiles, int act, int force_bn, int it
   for (int pass = 0; pass < 2 && best.bn == 0; ++pass)
     for (int i = 0; i < nc; ++i) {
       const int bn = cands[i];
+      if (whole_passes && bn % 32 != 0 && nc > 1) continue;  // LayerNorm statistics: no 32-column pass may overlap another
       const long long n_tiles = (N + bn - 1) / bn;
       const int n_mma = bn > 256 ? 2 : 1;
       for (int cg = 1; cg <= 2; ++cg) {
@@ -179,27 +189,45 @@ inline int splitk_enabled() {
   static int v = env_int("SDTF_SPLITK", 1);
   return v;
 }
-// The decision and the K partition depend on the layer (output pixels per sample, N, K) and NEVER on the batch size: a
-// sample's result must not depend on what it is batched with (fp32 partial sums round differently from one
-// accumulator), see test_full_size_batching_and_determinism.  Rule: the 8x8 level and below (<= 64 output pixels per
-// sample), spatial filters only (the linears run on token-shaped views that fold the batch into the pixel count), at
-// least 60 k-iterations, 4 ranges.
-inline SplitKPlan plan_splitk(int N, long long m_tiles, int iters, int act, bool bf16_out, long long pixels_per_sample, int taps) {
+// The decision and the K partition depend on the layer (output pixels per sample, N, K) and on the BATCH CLASS only
+// (small: <= kSmallBatch samples per call, i.e. one or two prompts with their CFG twins; large: anything above) — never
+// on the batch size inside a class: a sample's result must not depend on what it is batched with (fp32 partial sums
+// round differently from one accumulator), see test_full_size_batching_and_determinism.  Rules:
+//   * the 8x8 level and below (<= 64 output pixels per sample): always, 4 ranges;
+//   * the 16x16 level (<= 256 pixels per sample) in the small-batch class only: at UNet batch 2 those convs are 4 M tiles
+//     x 180 k-iterations — 32 CTAs walking a 60 us serial K loop; with 4 ranges 128 CTAs share it;
+//   * spatial filters only (the linears run on token-shaped views that fold the batch into the pixel count), >= 60
+//     k-iterations.
+// The N tile does NOT change any sum (every output element sees the same k order), so it is free to follow the batch:
+// the widest tile that still yields >= 96 CTAs (fewer operand bytes per FLOP), down to 64 columns when one M tile is all
+// there is (UNet batch 2 at 8x8: 80 CTAs stream the 29 MB of weights instead of 16).
+static constexpr int kSmallBatch = 4;
+inline SplitKPlan plan_splitk(int N, long long m_tiles, int iters, int act, bool bf16_out, long long pixels_per_sample, int taps,
+                              int batch) {
   SplitKPlan pl;
   if (!splitk_enabled() || !bf16_out || (act != ACT_NONE && act != ACT_SILU) || iters < 60 || N % 8 != 0) return pl;
-  if (pixels_per_sample > 64 || taps == 1) return pl;
-  static const int cands[4] = {320, 256, 160, 128};
+  if (taps == 1) return pl;
+  static const int small_on = env_int("SDTF_SPLITK_SMALL", 1);  // A/B: 0 = round-1 rule (8x8 level only)
+  const bool small = small_on && batch <= kSmallBatch;
+  if (pixels_per_sample > (small ? 256 : 64)) return pl;
+  static const int cands[5] = {320, 256, 160, 128, 64};
   static const int force_bn = env_int("SDTF_SPLITK_BN", 0), n_splits = env_int("SDTF_SPLITK_N", 4);  // tuning
   const int cg = m_tiles >= 2 ? 2 : 1;
+  const int iters_split = (iters + n_splits - 1) / n_splits;
+  const int splits = (iters + iters_split - 1) / iters_split;
+  int pick = 0;
   for (int bn : cands) {
     if (N % bn || (force_bn && bn != force_bn)) continue;
     const int n_mma = bn > 256 ? 2 : 1;
     if ((bn / n_mma) % 16 != 0 || (cg == 2 && (bn / n_mma / 2) % 8 != 0)) continue;
-    pl.iters_split = (iters + n_splits - 1) / n_splits;
-    pl.splits = (iters + pl.iters_split - 1) / pl.iters_split;
-    pl.cg = cg; pl.bn = bn; pl.n_mma = n_mma;
-    return pl;
+    pick = bn;  // the narrowest valid tile so far; stop at the widest one that fills the machine
+    const long long ctas = ((m_tiles + cg - 1) / cg) * (N / bn) * splits * cg;
+    if (ctas >= 96 || !small_on) break;
   }
+  if (!pick) return pl;
+  pl.iters_split = iters_split;
+  pl.splits = splits;
+  pl.cg = cg; pl.bn = pick; pl.n_mma = pick > 256 ? 2 : 1;
   return pl;
 }
 
@@ -255,7 +283,7 @@ inline size_t conv_splitk_floats(const ConvArgs& a) {
   const TileShape ts = choose_tile(a.outW, a.outH, a.a0.B);
   const long long m_tiles = (long long)ceil_div(a.outW, ts.bw) * ceil_div(a.outH, ts.bh) * ceil_div(a.a0.B, ts.bn);
   const int iters = w.kh * w.kw * (ceil_div(a.a0.C, 64) + (a.a1.p ? ceil_div(a.a1.C, 64) : 0));
-  const SplitKPlan sk = plan_splitk(w.N, m_tiles, iters, a.act, true, (long long)a.outH * a.outW, w.kh * w.kw);
+  const SplitKPlan sk = plan_splitk(w.N, m_tiles, iters, a.act, true, (long long)a.outH * a.outW, w.kh * w.kw, a.batch_class ? a.batch_class : a.a0.B);
   return sk.splits > 1 ? (size_t)sk.splits * a.a0.B * a.outH * a.outW * w.N : 0;
 }
 
@@ -284,6 +312,7 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   p.out = a.out; p.out_ld = a.out_ld; p.out_fp32 = a.out_fp32 ? 1 : 0;
   p.act = a.act;
   p.out_scale = a.out_scale;
+  p.ln_out = nullptr; p.ln_in = nullptr; p.ln_c1 = nullptr; p.ln_slots = 0; p.ln_rows = (long long)B * a.outH * a.outW; p.ln_inv_c = 0.f;
   const bool geglu = a.act == ACT_GEGLU;
   const int Nout = geglu ? w.N / 2 : w.N;
   const int iters = p.taps * (p.kc0 + p.kc1);
@@ -292,9 +321,9 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   const bool aligned = Nout % 8 == 0 && a.out_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.out) & 15) == 0 &&
                        (a.res == nullptr || (a.res_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a.res) & 15) == 0));
   if (!a.out_fp32 && !a.force_v1 && !gemm_v1_forced() && aligned) {
-    G3Plan plan = plan_gemm3(w.N, m_tiles, a.act, a.force_bn, iters);
+    G3Plan plan = plan_gemm3(w.N, m_tiles, a.act, a.force_bn, iters, a.ln_out != nullptr);
     SplitKPlan sk;
-    if (a.splitk_ws && !a.force_bn) sk = plan_splitk(w.N, m_tiles, iters, a.act, true, (long long)a.outH * a.outW, w.kh * w.kw);
+    if (a.splitk_ws && !a.force_bn) sk = plan_splitk(w.N, m_tiles, iters, a.act, true, (long long)a.outH * a.outW, w.kh * w.kw, a.batch_class ? a.batch_class : B);
     const bool split = sk.splits > 1;
     if (split) { plan.cg = sk.cg; plan.bn = sk.bn; plan.n_mma = sk.n_mma; plan.bufs = sk.bn > 256 ? 1 : 2; }
     p.BN = plan.bn;
@@ -309,6 +338,17 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
         p.bias = nullptr; p.temb = nullptr; p.res = nullptr; p.act = ACT_NONE; p.out_scale = 1.f;
       }
       if (geglu) SDTF_CHECK(w.geglu_half * 2 == p.BN && w.N % p.BN == 0, "GEGLU weight packing must match BN");
+      if (a.ln_out) {
+        SDTF_CHECK(!split && a.out_step == 1 && a.out_head_stride == 0 && !geglu && ncols % 32 == 0,
+                   "LayerNorm statistics: plain bf16 output in whole 32-column passes only");
+        p.ln_out = a.ln_out;
+        if (a.ln_slots_out) *a.ln_slots_out = 2 * n_tiles;
+      }
+      if (a.ln_in) {
+        SDTF_CHECK(w.ln_c1 != nullptr && w.ln_channels > 0 && a.ln_slots > 0 && !split && a.temb == nullptr && a.out_scale == 1.f,
+                   "LayerNorm-folded GEMM: weights must be packed with fold_ln, statistics supplied");
+        p.ln_in = a.ln_in; p.ln_slots = a.ln_slots; p.ln_c1 = w.ln_c1; p.ln_inv_c = 1.f / (float)w.ln_channels;
+      }
       Gemm3Extra x{};
       x.m_tiles = (int)m_tiles;
       x.n_tiles = n_tiles;
@@ -326,7 +366,7 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       x.splits = split ? sk.splits : 1;
       x.iters_split = split ? sk.iters_split : iters;
       x.partial = split ? a.splitk_ws : nullptr;
-      x.vec_rows = (a.temb && !split) ? p.bn : 1;
+      x.vec_rows = a.ln_in ? 2 : ((a.temb && !split) ? p.bn : 1);
       x.vec_width = ((geglu ? p.BN : ncols) + 31) / 32 * 32;
       const size_t vec_bytes = (size_t)2 * x.vec_rows * x.vec_width * 4;
       const int cg = plan.cg;
@@ -343,7 +383,17 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       CUtensorMap tmA0 = make_act_tmap(a.a0, p.bw, p.bh, p.bn, a.stride);
       CUtensorMap tmA1 = a.a1.p ? make_act_tmap(a.a1, p.bw, p.bh, p.bn, a.stride) : tmA0;
       CUtensorMap tmB = make_weight_tmap(w.w, w.K, w.N, p.taps, p.BN / plan.n_mma / cg);
-      CUtensorMap tmOut = make_epi_tmap(reinterpret_cast<const bf16*>(a.out), Nout, p.W, p.H, p.B, a.out_ld, p.bw, p.bh, p.bn, a.out_step);
+      x.head_stride = 0;
+      CUtensorMap tmOut;
+      if (a.out_head_stride > 0) {
+        SDTF_CHECK(a.out_head_stride % 32 == 0 && ncols % 32 == 0 && Nout % a.out_head_stride == 0 && a.out_step == 1 && !split && !a.res,
+                   "conv: head-clipped output needs 32-column passes that do not straddle heads");
+        x.head_stride = a.out_head_stride;
+        tmOut = make_epi_tmap_heads(reinterpret_cast<const bf16*>(a.out), a.out_head_d, a.out_head_stride, Nout / a.out_head_stride, p.W, p.H,
+                                    p.B, a.out_ld, p.bw, p.bh, p.bn);
+      } else {
+        tmOut = make_epi_tmap(reinterpret_cast<const bf16*>(a.out), Nout, p.W, p.H, p.B, a.out_ld, p.bw, p.bh, p.bn, a.out_step);
+      }
       CUtensorMap tmRes = (a.res && !split) ? make_epi_tmap(a.res, Nout, p.W, p.H, p.B, a.res_ld, p.bw, p.bh, p.bn) : tmOut;
       const long long units = ((m_tiles + cg - 1) / cg) * n_tiles * x.splits;
       const long long slots = sm_count() / cg;
@@ -391,7 +441,8 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
   }
 
   // ---- one tile per CTA (gemm.cuh): fp32 outputs, unaligned views ----
-  SDTF_CHECK(a.out_step == 1, "conv: strided output needs the TMA-store kernel (bf16, 16-byte aligned output)");
+  SDTF_CHECK(a.ln_in == nullptr && a.ln_out == nullptr, "conv: LayerNorm folding needs the TMA-store kernel");
+  SDTF_CHECK(a.out_step == 1 && a.out_head_stride == 0, "conv: strided / head-clipped output needs the TMA-store kernel (bf16, 16-byte aligned output)");
   p.BN = a.force_bn ? a.force_bn : choose_bn(w.N, m_tiles, a.act);
   if (geglu) SDTF_CHECK(w.geglu_half * 2 == p.BN && w.N % p.BN == 0, "GEGLU weight packing must match BN");
   SDTF_CHECK(p.BN % 16 == 0 && p.BN >= 16 && p.BN <= 256, "BN must be a multiple of 16 in [16,256]");

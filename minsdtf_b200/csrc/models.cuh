@@ -23,6 +23,7 @@ struct AttnW {
   int C = 0, d = 0, dstride = 0, hs = 0;  // hs = heads * dstride
   NormW gn, ln1, ln2, ln3;
   PackedWeight proj_in, qkv, out1, q2, kv2, out2, ff1, ff2, proj_out;
+  bool ln_fold = false;  // the three LayerNorms are folded into qkv / q2 / ff1 (gamma in the weights, statistics from the producers)
 };
 
 struct TimeW {
@@ -107,20 +108,30 @@ inline AttnW build_attn(WeightStore& ws, const std::string& p, int C) {
   AttnW a;
   a.C = C;
   a.d = C / kHeads;
-  a.dstride = a.d == 40 ? 64 : a.d;  // 40-wide heads are zero padded to 64 columns (one 128-byte TMA row)
+  // d = 40 heads sit 64 columns apart (one aligned 128-byte row per head and token for the attention kernels' TMA loads);
+  // the 24 padding columns are never written (clipped TMA store, Ctx::conv_heads) nor read (clipped load maps, attn.cuh).
+  // SDTF_HEAD_DENSE=1 (A/B): heads 40 columns apart — measured slower: the 80-byte rows cost the attention kernels more
+  // (unaligned L2 sectors on every K / V tile of every query tile) than the q | k | v GEMM saves.
+  static const int dense = getenv("SDTF_HEAD_DENSE") ? atoi(getenv("SDTF_HEAD_DENSE")) : 0;
+  a.dstride = (a.d == 40 && !dense) ? 64 : a.d;
   a.hs = kHeads * a.dstride;
   const std::string t = p + ".transformer_blocks.0";
   a.gn = ws.norm(p + ".norm");
   a.proj_in = ws.conv(p + ".proj_in");
+  // LayerNorm (diffusion_model.py:84,86,88) is not a kernel of its own: gamma is folded into the linear that follows, the
+  // row statistics come out of the epilogue of the GEMM that produces the LayerNorm's input, and the consumer's epilogue
+  // applies y = rstd (acc - mean c1) + c0.  SDTF_LN_FOLD=0 (A/B) keeps the separate LayerNorm kernels of round 1.
+  static const int fold_env = getenv("SDTF_LN_FOLD") ? atoi(getenv("SDTF_LN_FOLD")) : 1;
+  a.ln_fold = fold_env != 0;
   a.ln1 = ws.norm(t + ".norm1");
-  a.qkv = ws.stack({t + ".attn1.to_q", t + ".attn1.to_k", t + ".attn1.to_v"}, kHeads, a.d, a.dstride);
+  a.qkv = ws.stack({t + ".attn1.to_q", t + ".attn1.to_k", t + ".attn1.to_v"}, kHeads, a.d, a.dstride, a.ln_fold ? &a.ln1 : nullptr);
   a.out1 = ws.conv(t + ".attn1.to_out.0");
   a.ln2 = ws.norm(t + ".norm2");
-  a.q2 = ws.stack({t + ".attn2.to_q"}, kHeads, a.d, a.dstride);
+  a.q2 = ws.stack({t + ".attn2.to_q"}, kHeads, a.d, a.dstride, a.ln_fold ? &a.ln2 : nullptr);
   a.kv2 = ws.stack({t + ".attn2.to_k", t + ".attn2.to_v"}, kHeads, a.d, a.dstride);
   a.out2 = ws.conv(t + ".attn2.to_out.0");
   a.ln3 = ws.norm(t + ".norm3");
-  a.ff1 = ws.geglu(t + ".ff.net.0.proj");
+  a.ff1 = ws.geglu(t + ".ff.net.0.proj", a.ln_fold ? &a.ln3 : nullptr);
   a.ff2 = ws.conv(t + ".ff.net.2");
   a.proj_out = ws.conv(p + ".proj_out");
   return a;
@@ -306,16 +317,29 @@ inline void res_block(Ctx& c, const ResW& w, const View& x, const View& out, con
 inline void attentions(Ctx& c, const AttnW& w, const View& x, const View& out, const bf16* ctx_kv, int T) {
   const size_t m = c.ws->mark();
   const int B = x.B, HW = x.H * x.W, C = w.C;
+  const bool fold = w.ln_fold;
   View t = c.alloc_view(B, x.H, x.W, C);
   c.groupnorm(x, w.gn, false, t);
   View h0 = c.alloc_view(B, x.H, x.W, C);
-  c.conv(t, w.proj_in, h0);
-  View n = c.alloc_view(B, x.H, x.W, C);
+  // LayerNorm statistics: per row, (sum, sum of squares) partials written by the producing GEMM's epilogue
+  const long long rows = (long long)B * HW;
+  int slots = 2 * ((C + 63) / 64);  // upper bound for the dry run; the producer's launch reports how many it filled
+  float2* part = fold ? c.ws->alloc_n<float2>((size_t)slots * rows) : nullptr;
+  auto produce = [&](ConvArgs a) {  // a GEMM whose output feeds a LayerNorm
+    if (fold) { a.ln_out = part; a.ln_slots_out = &slots; }
+    c.conv(a);
+  };
+  auto consume = [&](ConvArgs a) {  // a GEMM whose A operand is a LayerNorm input
+    if (fold) { a.ln_in = part; a.ln_slots = slots; }
+    c.conv(a);
+  };
+  produce(Ctx::args(t, w.proj_in, h0));
+  View n = fold ? View() : c.alloc_view(B, x.H, x.W, C);
   View a = c.alloc_view(B, x.H, x.W, C);
   // --- self attention ---
-  c.layernorm(h0, w.ln1, n);
+  if (!fold) c.layernorm(h0, w.ln1, n);
   View qkv = c.alloc_view(B, x.H, x.W, 3 * w.hs);
-  c.conv(n.tokens(), w.qkv, qkv.tokens());
+  consume(Ctx::args_heads((fold ? h0 : n).tokens(), w.qkv, qkv.tokens(), w.d, w.dstride));
   AttnArgs aa;
   aa.q = qkv.p; aa.k = qkv.p + w.hs; aa.v = qkv.p + 2 * w.hs;
   aa.ldq = aa.ldk = aa.ldv = 3 * w.hs;
@@ -324,23 +348,23 @@ inline void attentions(Ctx& c, const AttnW& w, const View& x, const View& out, c
   c.attention(aa);
   View h1 = c.alloc_view(B, x.H, x.W, C);
   View h0t = h0.tokens();
-  c.conv(a.tokens(), w.out1, h1.tokens(), 1, -1, &h0t);
+  produce(Ctx::args(a.tokens(), w.out1, h1.tokens(), 1, -1, &h0t));
   // --- cross attention ---
-  c.layernorm(h1, w.ln2, n);
+  if (!fold) c.layernorm(h1, w.ln2, n);
   View q2 = qkv;  // reuse
   q2.C = w.hs; q2.ld = w.hs;
-  c.conv(n.tokens(), w.q2, q2.tokens());
+  consume(Ctx::args_heads((fold ? h1 : n).tokens(), w.q2, q2.tokens(), w.d, w.dstride));
   aa.q = q2.p; aa.ldq = w.hs;
   aa.k = ctx_kv; aa.v = ctx_kv + w.hs; aa.ldk = aa.ldv = 2 * w.hs;
   aa.Nk = T;
   c.attention(aa);
   View h2 = h0;  // h0 is dead after out1's residual read
   View h1t = h1.tokens();
-  c.conv(a.tokens(), w.out2, h2.tokens(), 1, -1, &h1t);
+  produce(Ctx::args(a.tokens(), w.out2, h2.tokens(), 1, -1, &h1t));
   // --- GEGLU feed-forward ---
-  c.layernorm(h2, w.ln3, n);
+  if (!fold) c.layernorm(h2, w.ln3, n);
   View g = c.alloc_view(B, x.H, x.W, 4 * C);
-  c.conv(n.tokens(), w.ff1, g.tokens(), 1, -1, nullptr, nullptr, 0, ACT_GEGLU);
+  consume(Ctx::args((fold ? h2 : n).tokens(), w.ff1, g.tokens(), 1, -1, nullptr, nullptr, 0, ACT_GEGLU));
   View h3 = h1;
   View h2t = h2.tokens();
   c.conv(g.tokens(), w.ff2, h3.tokens(), 1, -1, &h2t);

@@ -239,7 +239,7 @@ inline void init_norm_kernels() {
 
 // x: NHWC view (possibly a slice of a wider buffer); y dense [B][HW][C] (ldy may differ).  Returns the launch count.
 inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, const float* beta, bool silu, bf16* y,
-                            long long ldy, const GnScratch& sc) {
+                            long long ldy, const GnScratch& sc, int batch_class = 0) {
   SDTF_CHECK(x.C % 32 == 0 && x.C % 8 == 0, "GroupNorm needs C % 32 == 0");
   SDTF_CHECK(x.B <= kGnMaxBatch, "GroupNorm: batch too large for the statistics scratch");
   SDTF_CHECK(g_gn_resident_ctas > 0, "init_norm_kernels() was not called");
@@ -250,19 +250,27 @@ inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, 
   const int lanes = threads / vecs;
   const size_t smem = (size_t)lanes * x.C * 2 * sizeof(float);
   SDTF_CHECK(smem <= kGnMaxSmem, "GroupNorm: reduction scratch exceeds the shared-memory budget the occupancy was computed for");
-  // CTAs per sample: a function of (HW, C) only, so statistics do not depend on how samples are batched.
-  // ~32 KB of the sample per CTA (four 16-byte vectors per thread: one round of loads per phase) up to 16 CTAs — a UNet
-  // batch of 16 is then one co-resident round on 148 SMs.  The VAE's 16+ MB samples get 1 MB per CTA, 32 to 64 CTAs
+  // CTAs per sample: a function of (HW, C) and the BATCH CLASS only, so statistics do not depend on how samples are batched
+  // inside a class (gemm_host.cuh kSmallBatch: <= 4 samples per denoise step; `batch_class` carries the step's sample
+  // count when the call at hand only sees part of it — one branch of a CFG pair evaluated on its own).
+  // Large batches: ~32 KB of the sample per CTA (four 16-byte vectors per thread: one round of loads per phase) up to 16 CTAs —
+  // a UNet batch of 16 is then one co-resident round on 148 SMs; the VAE's 16+ MB samples get 1 MB per CTA, 32 to 64 CTAs
   // (measured: 128 CTAs per sample makes a single image's decode 1.3 ms faster but a batch of 8, walked in four rounds,
-  // 0.8 ms slower; 64 keeps the batch at two rounds).
+  // 0.8 ms slower; 64 keeps the batch at two rounds).  Small batches (one or two prompts: 2 x 16 CTAs left 116 SMs idle and
+  // a 2.6 MB sample took 35 us) cut the sample finer: up to 64 CTAs per sample.
+  static const int small_on = getenv("SDTF_GN_SMALL") ? atoi(getenv("SDTF_GN_SMALL")) : 1;  // A/B: 0 = round-1 partition
+  const int bc = batch_class > 0 ? batch_class : x.B;
+  const int cap = (small_on && bc <= 4) ? 64 : 16;
   const long long bytes = HW * x.C * 2;
   long long nblk = ceil_div_ll(bytes, 32 * 1024);
-  if (nblk > 16) {
-    nblk = 16;
+  if (nblk > cap) {
+    nblk = cap;
     if (bytes > (16LL << 20)) {
-      nblk = ceil_div_ll(bytes, 1024 * 1024);
-      if (nblk < 32) nblk = 32;
-      if (nblk > 64) nblk = 64;
+      const long long per = cap > 16 ? 256 * 1024 : 1024 * 1024;  // 1 MB per CTA, 256 KB in the small-batch class
+      nblk = ceil_div_ll(bytes, per);
+      const long long lo = 32, hi = cap > 64 ? cap : 64;
+      if (nblk < lo) nblk = lo;
+      if (nblk > hi) nblk = hi;
     }
   }
   if (nblk > HW / lanes) nblk = HW / lanes;
@@ -811,7 +819,8 @@ __global__ void to_uint8_kernel(const float* __restrict__ d, long long n, const 
 //   row_map[r] = source output channel for packed row n0 + r (or -1 for a zero row); scale folds constants.
 // ------------------------------------------------------------------------------------------------------
 __global__ void pack_weight_kernel(const float* __restrict__ src, int I, int taps, const int* __restrict__ row_map, int nrows,
-                                   int n0, int Ntot, int Kp, int k0, float scale, bf16* __restrict__ dst) {
+                                   int n0, int Ntot, int Kp, int k0, float scale, bf16* __restrict__ dst,
+                                   const float* __restrict__ kscale = nullptr /* [I]: LayerNorm gamma folded into the columns */) {
   const long long total = (long long)taps * nrows * I;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % I);
@@ -819,7 +828,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, int I, int tap
     const int row = (int)(r % nrows);
     const int t = (int)(r / nrows);
     const int so = row_map ? row_map[row] : row;
-    const float v = so >= 0 ? src[((long long)so * I + k) * taps + t] * scale : 0.f;
+    float v = so >= 0 ? src[((long long)so * I + k) * taps + t] * scale : 0.f;
+    if (kscale) v *= kscale[k];
     dst[((long long)t * Ntot + n0 + row) * Kp + k0 + k] = __float2bfloat16(v);
   }
 }
@@ -846,6 +856,32 @@ __global__ void pack_upconv_kernel(const float* __restrict__ src, int O, int I, 
     for (int y = ylo; y <= yhi; ++y)
       for (int x = xlo; x <= xhi; ++x) acc += w[y * 3 + x];
     dst[((long long)ct * O + o) * Kp + k] = __float2bfloat16(acc);
+  }
+}
+
+// LayerNorm folded into the linear that follows it: y = LN(x) W^T + b = rstd (x W'^T - mean c1) + c0 with
+//   W'[n][k] = bf16(gamma[k] W[n][k])   (packed by pack_weight_kernel with kscale = gamma)
+//   c1[n]    = sum_k W'[n][k]           (of the ROUNDED weights: it must cancel exactly what the tensor core summed)
+//   c0[n]    = b[n] + sum_k beta[k] W[n][k]
+// one warp per packed row; row_map as in pack_weight_kernel (-1: zero row)
+__global__ void ln_fold_consts_kernel(const float* __restrict__ src, int I, const int* __restrict__ row_map, int nrows, int n0,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ c1,
+                                      float* __restrict__ c0 /* in: bias (or 0), out: c0 */) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= nrows) return;
+  const int so = row_map ? row_map[row] : row;
+  float s1 = 0.f, s0 = 0.f;
+  if (so >= 0)
+    for (int k = lane; k < I; k += 32) {
+      const float w = src[(long long)so * I + k];
+      s1 += __bfloat162float(__float2bfloat16(w * gamma[k]));
+      s0 = fmaf(w, beta[k], s0);
+    }
+  s1 = warp_sum(s1);
+  s0 = warp_sum(s0);
+  if (lane == 0) {
+    c1[n0 + row] = s1;
+    c0[n0 + row] += s0;
   }
 }
 

@@ -797,6 +797,9 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
     // (Two half-batch passes in flight on two streams were measured and rejected in round 1: 18.45 ms per step against
     // 17.80 ms for the single 2B pass, profiles/r01_i_dual_stream_ab.log.)
     auto step = [&](Ctx& sc) {
+      // kernel schedules that depend on the batch class must see the step's whole sample count, however the CFG pair is
+      // evaluated (one 2B pass, two B passes, or one branch per GPU): split / two-pass runs then equal the batched one
+      sc.batch_class = cfg ? 2 * B : B;
       ++sc.launches;
       if (!sc.dry) {
         temb_select_kernel<<<ceil_div(Bt * ncat_u, 256), 256, 0, e->st>>>(tab_all_u, e->step_dev, ncat_u, Bt, tab_u);
@@ -872,6 +875,7 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
       c.launches += e->graph_launches * S;
     }
     c.ws->release(m_loop);
+    c.batch_class = 0;  // the decode below is a call of its own (B images)
     if (!c.dry) SDTF_CUDA(cudaEventRecord(e->ev[2], e->st));
 
     if (d->out_latent) e->emit(c, latent, olat);
@@ -1026,7 +1030,7 @@ int sdtf_bench_attention(sdtf_engine* e, int32_t batch, int32_t heads, int32_t n
   SDTF_CHECK(ms_per_launch != nullptr && reps >= 1, "bad arguments");
   float result = 0.f;
   e->run_sized([&](Ctx& c) {
-    const int dstride = d == 40 ? 64 : d, hs = heads * dstride;
+    const int dstride = d, hs = heads * dstride;
     // rotate over enough q/k/v/out sets that a launch does not find its operands in L2 (> 126 MB in total)
     const size_t set_bytes = ((size_t)batch * nq * (hs + heads * d) + (size_t)2 * batch * nk * hs) * 2;
     int nbuf = (int)((size_t)192 * 1024 * 1024 / (set_bytes ? set_bytes : 1)) + 1;
@@ -1085,7 +1089,7 @@ int sdtf_test_attention(sdtf_engine* e, const DLManagedTensor* q_t, const DLMana
   const bool legacy = heads < 0;  // negative head count selects the one-tile-per-CTA kernel
   if (legacy) heads = -heads;
   const int B = (int)q.shape[0], Nq = (int)q.shape[1], C = (int)q.shape[2], Nk = (int)k.shape[1];
-  const int d = C / heads, dstride = d == 40 ? 64 : d, hs = heads * dstride;
+  const int d = C / heads, dstride = d, hs = heads * dstride;
   expect_shape(k, {B, Nk, C}, "k");
   expect_shape(v, {B, Nk, C}, "v");
   expect_shape(out, {B, Nq, C}, "out");

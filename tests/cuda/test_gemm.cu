@@ -355,6 +355,7 @@ static bool check_upconv(int B, int H, int W, int C, int N, int ld_extra) {
 
 int main(int argc, char** argv) {
   bool bench = argc > 1 && !strcmp(argv[1], "bench");
+  const bool pick = argc > 2 && !strcmp(argv[1], "case");  // case <substr>: only the correctness cases whose name contains substr
   const char* only = argc > 2 ? argv[2] : nullptr;  // bench <substr>: run only the benchmark cases whose name contains substr
   init_gemm_kernels();
   std::vector<Case> cases = {
@@ -412,7 +413,11 @@ int main(int argc, char** argv) {
   };
   int fails = 0;
   try {
-    if (!only) {
+    if (pick) {
+      for (auto& c : cases)
+        if (strstr(c.name, only)) fails += run_case(c, false) ? 0 : 1;
+      if (strstr("upconv", only)) fails += check_upconv(2, 8, 8, 128, 128, 0) ? 0 : 1;
+    } else if (!only) {
       for (auto& c : cases) fails += run_case(c, false) ? 0 : 1;
       fails += check_batch_invariance(2, 8, 1280, 1280, true, false) ? 0 : 1;
       fails += check_batch_invariance(16, 8, 1280, 1280, false, true) ? 0 : 1;
@@ -423,7 +428,7 @@ int main(int argc, char** argv) {
       fails += check_upconv(3, 12, 20, 64, 96, 0) ? 0 : 1;      // ragged tiles, rectangular
       fails += check_upconv(1, 64, 64, 256, 256, 0) ? 0 : 1;    // VAE-sized grid
     }
-    if (bench)
+    if (bench && !pick)
       for (auto& c : bench_cases)
         if (!only || strstr(c.name, only)) fails += run_case(c, true) ? 0 : 1;
   } catch (const std::exception& e) {

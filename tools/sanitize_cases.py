@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""One small launch of every hand-written pipeline kernel, for `compute-sanitizer --tool racecheck|synccheck|memcheck`
+(tools/gpu_sanitize.sh): attention variants (attn2h d=40 self, attn2q d=80 self, xattn d=40 / d=80 cross, attn d=160,
+vattn d=512), the one-kernel GroupNorm, LayerNorm, and the fused CFG + scheduler step.  Sizes are tiny: the sanitizer
+slows kernels by two orders of magnitude."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from minsdtf_b200 import _lib  # noqa: E402
+from minsdtf_b200._lib import StepCoef  # noqa: E402
+from minsdtf_b200.engine import Engine  # noqa: E402
+
+
+def main():
+    e = Engine(0)
+    rng = np.random.default_rng(0)
+    dl = _lib.DL()
+    for (B, nq, nk, heads, d) in [(1, 256, 256, 2, 40), (1, 256, 256, 2, 80), (1, 256, 77, 2, 40), (1, 256, 77, 2, 80), (1, 128, 128, 2, 160),
+                                  (1, 256, 256, 1, 512)]:
+        q = rng.standard_normal((B, nq, heads * d)).astype(np.float32)
+        k = rng.standard_normal((B, nk, heads * d)).astype(np.float32)
+        v = rng.standard_normal((B, nk, heads * d)).astype(np.float32)
+        out = np.empty_like(q)
+        e._check(e._lib.sdtf_test_attention(e._h, dl(q), dl(k), dl(v), heads, dl(out)))
+        assert np.isfinite(out).all()
+        print("attention", (B, nq, nk, heads, d), "ok", flush=True)
+    for (shape, mode) in [((2, 16, 16, 320), 1), ((1, 8, 8, 1280), 0), ((1, 16, 16, 320), 2)]:
+        x = rng.standard_normal(shape).astype(np.float32)
+        g, b = np.ones(shape[-1], np.float32), np.zeros(shape[-1], np.float32)
+        out = np.empty_like(x)
+        e._check(e._lib.sdtf_test_norm(e._h, dl(x), dl(g), dl(b), mode, dl(out)))
+        assert np.isfinite(out).all()
+        print("norm", shape, mode, "ok", flush=True)
+    eu, ec, x = (rng.standard_normal((2, 16, 16, 4)).astype(np.float32) for _ in range(3))
+    got = e.cfg_sched_step(eu, ec, x, StepCoef(7.5, 0.7, 0.9, 0.1, 0.0, 0, 0))
+    assert np.isfinite(got).all()
+    print("cfg_sched ok", flush=True)
+    e.close()
+
+
+if __name__ == "__main__":
+    main()
