@@ -1,6 +1,8 @@
 // engine.cuh — engine state: device arena, weight store + packing, and the launch context every model graph
 // issues its kernels through (dry-run aware, so the workspace high-water mark is measured before anything runs).
 #pragma once
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges are no-ops unless a tool (ncu --nvtx, nsys) injects itself
+
 #include <map>
 #include <memory>
 #include <string>
@@ -139,8 +141,19 @@ struct Ctx {
   GnScratch gn;
   int batch_class = 0;  // samples per denoise step (both CFG branches) when calls see one branch at a time; 0: the call's own batch
 
+  // SDTF_NVTX=1: every operator launch sits in an NVTX range "kind shape" (e.g. "conv 16x64x64 320->320 k3 s1 +res"), so a
+  // profile can be filtered by operator (`ncu --nvtx --nvtx-include "attn*"`) instead of by kernel name and launch index
+  static bool nvtx_on() {
+    static const int v = getenv("SDTF_NVTX") ? atoi(getenv("SDTF_NVTX")) : 0;
+    return v != 0;
+  }
   template <class F>
   void traced(const char* kind, const std::string& shape, double flop, double bytes, F&& f) {
+    struct Range {
+      bool on;
+      Range(bool o, const char* k, const std::string& s) : on(o) { if (on) nvtxRangePushA((std::string(k) + " " + s).c_str()); }
+      ~Range() { if (on) nvtxRangePop(); }
+    } range(nvtx_on() && !dry, kind, shape);
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (!trace_on() || dry || (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)) {
       f();

@@ -49,8 +49,8 @@ struct GemmParams {
   int act;
   float out_scale;            // applied to the accumulator before bias (1.0 = off)
   // ---- LayerNorm folded into the GEMMs around it (gemm3.cuh only; see DESIGN.md "LayerNorm") ----
-  // producer side: this GEMM's OUTPUT rows are the input of a LayerNorm: per row, sum and sum of squares of the (bf16-rounded)
-  // outputs of the tile's even / odd 32-column passes -> ln_out[(2 n_tile + parity) * ln_rows + row]
+  // producer side: this GEMM's OUTPUT rows are the input of a LayerNorm: per row and 32-column pass, sum and sum of squares
+  // of the (bf16-rounded) outputs -> ln_out[(column / 32) * ln_rows + row]
   float2* ln_out;
   // consumer side: this GEMM's A operand is the UN-normalised LayerNorm input; the weights carry gamma, and the epilogue
   // applies y = rstd (acc - mean c1[n]) + c0[n] with the row statistics summed from ln_slots partials

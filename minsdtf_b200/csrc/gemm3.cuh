@@ -368,7 +368,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         ln_a = rsqrtf(var + 1e-5f);
         ln_b = -ln_a * mean;
       }
-      float ln_s1 = 0.f, ln_s2 = 0.f;
+
       // this tile's per-column vector (bias, + the time-embedding row of each sample the tile spans): fetched from
       // global BEFORE waiting for the accumulator so the latency hides behind the main loop, then staged in smem
       float4 pre[4];
@@ -527,6 +527,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = qgelu_f(f[i]);
         }
+        float ln_s1 = 0.f, ln_s2 = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 o;
@@ -535,7 +536,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           o.z = pack_bf16(f[8 * c + 4], f[8 * c + 5]);
           o.w = pack_bf16(f[8 * c + 6], f[8 * c + 7]);
           *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) = o;
-          if (p.ln_out) {  // statistics of what the consumer will read: the bf16-rounded values
+          if (p.ln_out) {  // statistics of what the consumer will read: the bf16-rounded values, summed in column order
             const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -546,17 +547,14 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             }
           }
         }
+        // LayerNorm producer: one (sum, sum of squares) slot per 32-column pass, indexed by the pass's GLOBAL column
+        // (column / 32).  Coarser slots (per N tile) would be cheaper but their grouping follows BN, which follows the
+        // number of M tiles, i.e. the batch: a sample's statistics must not depend on what it is batched with.
+        if (p.ln_out && ln_m >= 0)
+          p.ln_out[(long long)((n_tile * ncols + tc) >> 5) * p.ln_rows + ln_m] = make_float2(ln_s1, ln_s2);
         fence_proxy_async_smem();  // staged row (generic proxy) -> visible to the TMA store (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(stg_bar(buf));
-      }
-      // LayerNorm producer: this thread's passes of the tile all have the parity of ps0 -> slot (n_tile, parity).  A tile
-      // whose passes of one parity do not exist (a single 32-column pass) still writes that slot, as zeros, from the set
-      // that drew the blank.  (The column grouping must not depend on which WARP SET handled a pass: that follows the
-      // CTA-local tile counter, hence the grid size, hence the batch.)
-      if (p.ln_out && ln_m >= 0) {
-        const int par = ps0 & 1;
-        p.ln_out[(long long)(2 * n_tile + par) * p.ln_rows + ln_m] = make_float2(ln_s1, ln_s2);
       }
     }
     if (prof_on && threadIdx.x == 128) { prof[8] = w_tfull; prof[9] = w_grant; prof[10] = clock64() - t_start; prof[11] = lt; }

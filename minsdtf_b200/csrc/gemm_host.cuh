@@ -36,7 +36,7 @@ struct ConvArgs {
   int out_head_d = 0, out_head_stride = 0;  // > 0: output columns are heads `out_head_stride` apart, only the first `out_head_d` are stored
   // LayerNorm folded into the surrounding GEMMs (gemm.cuh GemmParams::ln_*)
   float2* ln_out = nullptr;      // producer: per-row partial (sum, sum of squares) slots of the output, [slots][pixels]
-  int* ln_slots_out = nullptr;   //           number of slots this launch filled (2 per N tile)
+  int* ln_slots_out = nullptr;   //           number of slots this launch filled (one per 32 output columns)
   const float2* ln_in = nullptr; // consumer: partials of its A operand's rows (weights must have been packed with fold_ln)
   int ln_slots = 0;
   int batch_class = 0;  // samples of the whole denoise step when this call only sees part of them (0: a0.B); see plan_splitk
@@ -339,10 +339,10 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       }
       if (geglu) SDTF_CHECK(w.geglu_half * 2 == p.BN && w.N % p.BN == 0, "GEGLU weight packing must match BN");
       if (a.ln_out) {
-        SDTF_CHECK(!split && a.out_step == 1 && a.out_head_stride == 0 && !geglu && ncols % 32 == 0,
+        SDTF_CHECK(!split && a.out_step == 1 && a.out_head_stride == 0 && !geglu && ncols % 32 == 0 && Nout % 32 == 0,
                    "LayerNorm statistics: plain bf16 output in whole 32-column passes only");
         p.ln_out = a.ln_out;
-        if (a.ln_slots_out) *a.ln_slots_out = 2 * n_tiles;
+        if (a.ln_slots_out) *a.ln_slots_out = Nout / 32;
       }
       if (a.ln_in) {
         SDTF_CHECK(w.ln_c1 != nullptr && w.ln_channels > 0 && a.ln_slots > 0 && !split && a.temb == nullptr && a.out_scale == 1.f,

@@ -23,7 +23,8 @@ struct AttnW {
   int C = 0, d = 0, dstride = 0, hs = 0;  // hs = heads * dstride
   NormW gn, ln1, ln2, ln3;
   PackedWeight proj_in, qkv, out1, q2, kv2, out2, ff1, ff2, proj_out;
-  bool ln_fold = false;  // the three LayerNorms are folded into qkv / q2 / ff1 (gamma in the weights, statistics from the producers)
+  bool ln_fold = false;  // the LayerNorms are folded into qkv / q2 / ff1 (gamma in the weights, statistics from the producers)
+  bool ln3_fold = false; // ... including the one in front of the GEGLU projection (SDTF_LN_FOLD=2 keeps that one a kernel)
 };
 
 struct TimeW {
@@ -108,11 +109,13 @@ inline AttnW build_attn(WeightStore& ws, const std::string& p, int C) {
   AttnW a;
   a.C = C;
   a.d = C / kHeads;
-  // d = 40 heads sit 64 columns apart (one aligned 128-byte row per head and token for the attention kernels' TMA loads);
-  // the 24 padding columns are never written (clipped TMA store, Ctx::conv_heads) nor read (clipped load maps, attn.cuh).
-  // SDTF_HEAD_DENSE=1 (A/B): heads 40 columns apart — measured slower: the 80-byte rows cost the attention kernels more
-  // (unaligned L2 sectors on every K / V tile of every query tile) than the q | k | v GEMM saves.
-  static const int dense = getenv("SDTF_HEAD_DENSE") ? atoi(getenv("SDTF_HEAD_DENSE")) : 0;
+  // Heads are stored densely (d = 40: 80-byte rows); the attention kernels' 4-D TMA maps clip a 64-column box at the head
+  // size and zero-fill the rest in shared memory, so nothing is padded in HBM: the q | k | v GEMM at the 64x64 level writes
+  // 126 MB instead of 201 MB.  SDTF_HEAD_DENSE=0 (A/B) puts d = 40 heads 64 columns apart (one aligned 128-byte row per
+  // head and token) with the padding neither written (clipped 5-D TMA store, Ctx::conv_heads; SDTF_HEAD_CLIP=0 writes
+  // it) nor read.  Same box, UNet step at batch 16: dense 17.65 ms, padded + clipped 17.95 ms, padded + written 17.91 ms
+  // (profiles/r02_e_ab.log).
+  static const int dense = getenv("SDTF_HEAD_DENSE") ? atoi(getenv("SDTF_HEAD_DENSE")) : 1;
   a.dstride = (a.d == 40 && !dense) ? 64 : a.d;
   a.hs = kHeads * a.dstride;
   const std::string t = p + ".transformer_blocks.0";
@@ -120,9 +123,13 @@ inline AttnW build_attn(WeightStore& ws, const std::string& p, int C) {
   a.proj_in = ws.conv(p + ".proj_in");
   // LayerNorm (diffusion_model.py:84,86,88) is not a kernel of its own: gamma is folded into the linear that follows, the
   // row statistics come out of the epilogue of the GEMM that produces the LayerNorm's input, and the consumer's epilogue
-  // applies y = rstd (acc - mean c1) + c0.  SDTF_LN_FOLD=0 (A/B) keeps the separate LayerNorm kernels of round 1.
-  static const int fold_env = getenv("SDTF_LN_FOLD") ? atoi(getenv("SDTF_LN_FOLD")) : 1;
+  // applies y = rstd (acc - mean c1) + c0.  Default (2): norm1 -> q|k|v and norm2 -> q are folded, norm3 in front of the
+  // GEGLU projection stays a kernel — that GEMM is epilogue-bound already and the extra FMAs cost more than the kernel
+  // saves.  Same box, UNet step at batch 16 (profiles/r02_f_ab.log): 2 -> 17.66 ms, 1 (all three folded) -> 17.83 ms,
+  // 0 (round 1: three LayerNorm kernels per block) with the other round-2 switches off too -> 18.00 ms.
+  static const int fold_env = getenv("SDTF_LN_FOLD") ? atoi(getenv("SDTF_LN_FOLD")) : 2;
   a.ln_fold = fold_env != 0;
+  a.ln3_fold = fold_env == 1;
   a.ln1 = ws.norm(t + ".norm1");
   a.qkv = ws.stack({t + ".attn1.to_q", t + ".attn1.to_k", t + ".attn1.to_v"}, kHeads, a.d, a.dstride, a.ln_fold ? &a.ln1 : nullptr);
   a.out1 = ws.conv(t + ".attn1.to_out.0");
@@ -131,7 +138,7 @@ inline AttnW build_attn(WeightStore& ws, const std::string& p, int C) {
   a.kv2 = ws.stack({t + ".attn2.to_k", t + ".attn2.to_v"}, kHeads, a.d, a.dstride);
   a.out2 = ws.conv(t + ".attn2.to_out.0");
   a.ln3 = ws.norm(t + ".norm3");
-  a.ff1 = ws.geglu(t + ".ff.net.0.proj", a.ln_fold ? &a.ln3 : nullptr);
+  a.ff1 = ws.geglu(t + ".ff.net.0.proj", a.ln3_fold ? &a.ln3 : nullptr);
   a.ff2 = ws.conv(t + ".ff.net.2");
   a.proj_out = ws.conv(p + ".proj_out");
   return a;
@@ -323,7 +330,7 @@ inline void attentions(Ctx& c, const AttnW& w, const View& x, const View& out, c
   View h0 = c.alloc_view(B, x.H, x.W, C);
   // LayerNorm statistics: per row, (sum, sum of squares) partials written by the producing GEMM's epilogue
   const long long rows = (long long)B * HW;
-  int slots = 2 * ((C + 63) / 64);  // upper bound for the dry run; the producer's launch reports how many it filled
+  int slots = C / 32;  // one (sum, sum of squares) pair per row and 32 columns, written by the producing GEMM's epilogue
   float2* part = fold ? c.ws->alloc_n<float2>((size_t)slots * rows) : nullptr;
   auto produce = [&](ConvArgs a) {  // a GEMM whose output feeds a LayerNorm
     if (fold) { a.ln_out = part; a.ln_slots_out = &slots; }
@@ -334,7 +341,8 @@ inline void attentions(Ctx& c, const AttnW& w, const View& x, const View& out, c
     c.conv(a);
   };
   produce(Ctx::args(t, w.proj_in, h0));
-  View n = fold ? View() : c.alloc_view(B, x.H, x.W, C);
+  const bool fold3 = w.ln3_fold;
+  View n = (fold && fold3) ? View() : c.alloc_view(B, x.H, x.W, C);
   View a = c.alloc_view(B, x.H, x.W, C);
   // --- self attention ---
   if (!fold) c.layernorm(h0, w.ln1, n);
@@ -360,11 +368,13 @@ inline void attentions(Ctx& c, const AttnW& w, const View& x, const View& out, c
   c.attention(aa);
   View h2 = h0;  // h0 is dead after out1's residual read
   View h1t = h1.tokens();
-  produce(Ctx::args(a.tokens(), w.out2, h2.tokens(), 1, -1, &h1t));
+  if (fold3) produce(Ctx::args(a.tokens(), w.out2, h2.tokens(), 1, -1, &h1t));
+  else c.conv(a.tokens(), w.out2, h2.tokens(), 1, -1, &h1t);
   // --- GEGLU feed-forward ---
-  if (!fold) c.layernorm(h2, w.ln3, n);
+  if (!fold3) c.layernorm(h2, w.ln3, n);
   View g = c.alloc_view(B, x.H, x.W, 4 * C);
-  consume(Ctx::args((fold ? h2 : n).tokens(), w.ff1, g.tokens(), 1, -1, nullptr, nullptr, 0, ACT_GEGLU));
+  if (fold3) consume(Ctx::args(h2.tokens(), w.ff1, g.tokens(), 1, -1, nullptr, nullptr, 0, ACT_GEGLU));
+  else c.conv(n.tokens(), w.ff1, g.tokens(), 1, -1, nullptr, nullptr, 0, ACT_GEGLU);
   View h3 = h1;
   View h2t = h2.tokens();
   c.conv(g.tokens(), w.ff2, h3.tokens(), 1, -1, &h2t);

@@ -228,3 +228,43 @@ def test_engine_creation_fails_loudly_without_gpu():
     with pytest.raises(EngineError) as ei:
         Engine(0)
     assert "no CPU fallback" in str(ei.value) or "no fallback" in str(ei.value)
+
+
+def test_read_checkpoint_formats(tmp_path):
+    """.safetensors, a torch pickle, and a pickle wrapped in {"state_dict": ...} all come back as {key: tensor}
+    (ckpt_loader.py:2139-2145; `control_sd15_canny.pth` and `.ckpt` files are pickles)"""
+    import torch
+    from minsdtf_b200 import synth
+    from minsdtf_b200.engine import Engine
+    sd = {k: v for k, v in list(synth.make_state_dict("hintnet").items())[:6]}
+    synth.save_safetensors(sd, str(tmp_path / "a.safetensors"))
+    torch.save(sd, str(tmp_path / "b.pth"))
+    torch.save({"state_dict": sd, "epoch": 3}, str(tmp_path / "c.ckpt"))
+    for name in ("a.safetensors", "b.pth", "c.ckpt"):
+        got = Engine.read_checkpoint(str(tmp_path / name))
+        assert set(got) == set(sd)
+        assert all(torch.equal(got[k], sd[k]) for k in sd)
+
+
+def test_lora_names_and_merge():
+    """kohya module names -> the diffusers-style aliases of the reference's UNET_KEY_MAPPING (ckpt_loader.py:2231-2272), and
+    the merge adds (alpha / rank) * up . down to the tensor the alias belongs to"""
+    import torch
+    from minsdtf_b200 import keys as K, lora, synth
+    assert lora.unet_param_name("lora_unet_down_blocks_0_attentions_1_transformer_blocks_0_attn2_to_out_0") == \
+        "down_blocks.0.attentions.1.transformer_blocks.0.attn2.to_out.0.weight"
+    assert lora.unet_param_name("lora_unet_mid_block_resnets_1_time_emb_proj") == "mid_block.resnets.1.time_emb_proj.weight"
+    assert lora.unet_param_name("lora_unet_up_blocks_2_upsamplers_0_conv") == "up_blocks.2.upsamplers.0.conv.weight"
+    assert lora.unet_param_name("lora_unet_conv_in") is None
+    assert lora.text_param_name("lora_te_text_model_encoder_layers_11_self_attn_out_proj") == \
+        "text_model.encoder.layers.11.self_attn.out_proj.weight"
+    te, un = lora.load_lora(synth.make_lora_state_dict())
+    alias = K.unet_alias_map()
+    assert set(un) <= set(alias.values()) and len(te) == 12
+    name = next(iter(un))
+    key = next(k for k, a in alias.items() if a == name)
+    base = {key: torch.zeros(K.unet_keys()[key])}
+    merged, n, unused = lora.merge(base, un, alias)
+    assert n == 1 and len(unused) == len(un) - 1 and np.allclose(merged[key].numpy(), un[name])
+    with pytest.raises(ValueError):
+        lora.merge({key: torch.zeros(3, 3)}, un, alias)
