@@ -68,7 +68,19 @@ static constexpr int kG3Threads = 384;
 static constexpr int kG3MaxBufs = 8;              // staging buffers: x.nbufs of them (4, or 8 when residual tiles must be prefetched deep)
 static constexpr uint32_t kG3BufBytes = 128 * 64; // 128 rows x 32 bf16
 
-template <int CG>
+// MODE: which epilogue variants an instantiation carries.  The general kernel (every variant behind run-time flags) is 5 800
+// SASS instructions (93 KB) and ncu showed its epilogue warps stalled on instruction fetch (no_inst 18 % of the samples of
+// the HBM-bound 1x1 GEMMs): a launch only ever needs one variant, so each gets its own, smaller kernel.  Same box, isolated:
+// 320->320 +res @64x64 39 -> 33 us, q|k|v 89 -> 72 us, 3x3 320->320 96 -> 91 us (profiles/r02_j_lean_bench_cases.log).
+enum : int {
+  G3_GENERAL = 0,     // everything: split-K partial sums, quick-GELU, per-role profiler, and all of the below
+  G3_LEAN = 1,        // bias / time embedding / residual / SiLU
+  G3_GEGLU = 2,       // + GEGLU gate
+  G3_LN_PRODUCE = 3,  // + LayerNorm statistics of the output rows
+  G3_LN_APPLY = 4,    // + LayerNorm applied to the accumulator (gamma folded into the weights)
+  G3_GEGLU_LN = 5,    // GEGLU gate on a LayerNorm-folded projection (SDTF_LN_FOLD=1)
+};
+template <int CG, int MODE = G3_GENERAL>
 __global__ void __launch_bounds__(kG3Threads, 1)
 conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
@@ -102,9 +114,12 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int iters = p.taps * kchunks;
   const int m_units = (x.m_tiles + CG - 1) / CG;
   const int total_units = m_units * x.n_tiles * x.splits;
-  const bool partial_mode = x.partial != nullptr;
+  constexpr bool kAll = MODE == G3_GENERAL;
+  constexpr bool kGeglu = kAll || MODE == G3_GEGLU || MODE == G3_GEGLU_LN, kLnOut = kAll || MODE == G3_LN_PRODUCE,
+                 kLnIn = kAll || MODE == G3_LN_APPLY || MODE == G3_GEGLU_LN;
+  const bool partial_mode = kAll && x.partial != nullptr;
   const int unit0 = (int)blockIdx.x / CG, unit_step = (int)gridDim.x / CG;
-  const bool prof_on = x.prof != nullptr;
+  const bool prof_on = kAll && x.prof != nullptr;
   long long* prof = prof_on ? x.prof + (long long)blockIdx.x * 16 : nullptr;
   const long long t_start = prof_on ? clock64() : 0;
 
@@ -263,7 +278,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ===== store warp: TMA stores of staged sub-tiles; grants staging buffers (with the residual tile when there is one)
     // (split-K partial sums leave straight from the epilogue warps' registers: nothing to stage)
     if (!partial_mode && elect_one()) {
-      const bool geglu = (p.act == ACT_GEGLU);
+      const bool geglu = kGeglu && (p.act == ACT_GEGLU);
       const int ncols = x.ncols;
       const int passes = (ncols + 31) >> 5;
       const bool has_res = p.res != nullptr;
@@ -321,9 +336,10 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int set = (warp - 4) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const bool geglu = (p.act == ACT_GEGLU);
+    const bool geglu = kGeglu && (p.act == ACT_GEGLU);
     const int ncols = x.ncols;
     const int Nout = geglu ? p.N / 2 : p.N;
+    float2* const ln_out = kLnOut ? p.ln_out : nullptr;
     const int passes = (ncols + 31) >> 5;
     const bool has_res = p.res != nullptr;
     const int sw = (row >> 1) & 3;  // 64-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
@@ -331,8 +347,8 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
     long long w_tfull = 0, w_grant = 0;
     const int et = (int)threadIdx.x - 128;  // 0..255 (set 0: 0..127)
-    const bool has_vec = p.bias != nullptr || p.temb != nullptr || p.ln_c1 != nullptr;
-    const bool ln_apply = p.ln_in != nullptr;
+    const bool ln_apply = kLnIn && p.ln_in != nullptr;
+    const bool has_vec = p.bias != nullptr || p.temb != nullptr || ln_apply;
     const int rpb = 1 << x.log_rows_per_b;
     const int vrows = x.vec_rows, vwidth = x.vec_width;
     const int Nvec = geglu ? p.N : Nout;
@@ -351,7 +367,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (ln_apply) vr = 0;              // LayerNorm consumer: vector row 0 = c0 (bias), row 1 = c1
       // global pixel index of this thread's row (LayerNorm statistics are indexed by it)
       long long ln_m = -1;
-      if (ln_apply || p.ln_out) {
+      if (ln_apply || ln_out) {
         const int rr = row & (rpb - 1);
         const int pb = b0 + (row >> x.log_rows_per_b), py = y0 + rr / p.bw, px = x0 + rr % p.bw;
         if (pb < p.B && py < p.H && px < p.W) ln_m = ((long long)pb * p.H + py) * p.W + px;
@@ -523,7 +539,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = silu_f(f[i]);
         }
-        if (p.act == ACT_QGELU) {
+        if (kAll && p.act == ACT_QGELU) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = qgelu_f(f[i]);
         }
@@ -536,7 +552,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           o.z = pack_bf16(f[8 * c + 4], f[8 * c + 5]);
           o.w = pack_bf16(f[8 * c + 6], f[8 * c + 7]);
           *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) = o;
-          if (p.ln_out) {  // statistics of what the consumer will read: the bf16-rounded values, summed in column order
+          if (ln_out) {  // statistics of what the consumer will read: the bf16-rounded values, summed in column order
             const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -550,8 +566,8 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // LayerNorm producer: one (sum, sum of squares) slot per 32-column pass, indexed by the pass's GLOBAL column
         // (column / 32).  Coarser slots (per N tile) would be cheaper but their grouping follows BN, which follows the
         // number of M tiles, i.e. the batch: a sample's statistics must not depend on what it is batched with.
-        if (p.ln_out && ln_m >= 0)
-          p.ln_out[(long long)((n_tile * ncols + tc) >> 5) * p.ln_rows + ln_m] = make_float2(ln_s1, ln_s2);
+        if (ln_out && ln_m >= 0)
+          ln_out[(long long)((n_tile * ncols + tc) >> 5) * p.ln_rows + ln_m] = make_float2(ln_s1, ln_s2);
         fence_proxy_async_smem();  // staged row (generic proxy) -> visible to the TMA store (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(stg_bar(buf));

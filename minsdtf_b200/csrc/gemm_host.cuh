@@ -273,6 +273,16 @@ inline void init_gemm_kernels() {
   SDTF_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<1, G3_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<2, G3_LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<1, G3_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<2, G3_GEGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<1, G3_LN_PRODUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<2, G3_LN_PRODUCE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<1, G3_GEGLU_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<2, G3_GEGLU_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<1, G3_LN_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+  SDTF_CUDA(cudaFuncSetAttribute(conv_gemm3_kernel<2, G3_LN_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
   sm_count();
 }
 
@@ -408,8 +418,31 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
         SDTF_CUDA(cudaMemsetAsync(prof_buf, 0, sizeof(long long) * 16 * 160, stream));
         x.prof = prof_buf;
       }
-      if (cg == 2) launch_pdl(conv_gemm3_kernel<2>, dim3(grid), dim3(kG3Threads), smem, stream, 2, tmA0, tmA1, tmB, tmOut, tmRes, p, x);
-      else launch_pdl(conv_gemm3_kernel<1>, dim3(grid), dim3(kG3Threads), smem, stream, 1, tmA0, tmA1, tmB, tmOut, tmRes, p, x);
+      // one instantiation per epilogue variant (gemm3.cuh MODE); SDTF_GEMM_LEAN=0 (A/B): every launch on the general kernel
+      static const int lean_on = env_int("SDTF_GEMM_LEAN", 1);
+      const bool plain_act = a.act == ACT_NONE || a.act == ACT_SILU;
+      int mode = G3_GENERAL;
+      if (lean_on && !split && !profile) {
+        if (geglu && !a.ln_in && !a.ln_out) mode = G3_GEGLU;
+        else if (geglu && a.ln_in && !a.ln_out) mode = G3_GEGLU_LN;
+        else if (plain_act && a.ln_out && !a.ln_in) mode = G3_LN_PRODUCE;
+        else if (plain_act && a.ln_in && !a.ln_out) mode = G3_LN_APPLY;
+        else if (plain_act && !a.ln_in && !a.ln_out) mode = G3_LEAN;
+      }
+#define SDTF_G3_LAUNCH(M)                                                                                                        \
+  do {                                                                                                                           \
+    if (cg == 2) launch_pdl(conv_gemm3_kernel<2, M>, dim3(grid), dim3(kG3Threads), smem, stream, 2, tmA0, tmA1, tmB, tmOut, tmRes, p, x); \
+    else launch_pdl(conv_gemm3_kernel<1, M>, dim3(grid), dim3(kG3Threads), smem, stream, 1, tmA0, tmA1, tmB, tmOut, tmRes, p, x);        \
+  } while (0)
+      switch (mode) {
+        case G3_LEAN: SDTF_G3_LAUNCH(G3_LEAN); break;
+        case G3_GEGLU: SDTF_G3_LAUNCH(G3_GEGLU); break;
+        case G3_GEGLU_LN: SDTF_G3_LAUNCH(G3_GEGLU_LN); break;
+        case G3_LN_PRODUCE: SDTF_G3_LAUNCH(G3_LN_PRODUCE); break;
+        case G3_LN_APPLY: SDTF_G3_LAUNCH(G3_LN_APPLY); break;
+        default: SDTF_G3_LAUNCH(G3_GENERAL); break;
+      }
+#undef SDTF_G3_LAUNCH
       SDTF_CUDA(cudaGetLastError());
       if (split) {
         const long long M = (long long)p.B * p.H * p.W;
