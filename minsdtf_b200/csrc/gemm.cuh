@@ -65,8 +65,9 @@ static constexpr int kBM = 128;
 static constexpr int kBK = 64;
 static constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
-__device__ __forceinline__ float qgelu_f(float x) { return x / (1.f + __expf(-1.702f * x)); }
+// (__fdividef: the IEEE division's slow-path call + check per element was 32 CALL / FCHK pairs in every epilogue pass)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float qgelu_f(float x) { return __fdividef(x, 1.f + __expf(-1.702f * x)); }
 // tanh-approximation GELU exactly as the reference spells it (diffusion_model.py:150-153)
 __device__ __forceinline__ float gelu_tanh_f(float g) {
   float u = g * 0.7978845608f * (1.f + 0.044715f * g * g);

@@ -34,6 +34,22 @@ __device__ __forceinline__ float gelu_tanh_fast(float g) {
   return 0.5f * g * (1.f + tanh_approx(u));
 }
 
+// u / d for the small non-negative integers of the tile bookkeeping as one multiply-high: q = (u * ceil(2^32 / d)) >> 32,
+// exact while u * d < 2^32 (the host checks it).  A run-time integer division is ~25 SASS instructions, and the tile
+// decode has six of them at four call sites: a sixth of the kernel's code before this.
+struct FastDiv {
+  uint32_t mul = 0, d = 1;
+#ifdef __CUDACC__
+  __device__ __forceinline__ int div(int u) const { return d == 1 ? u : (int)__umulhi((uint32_t)u, mul); }
+#endif
+  static FastDiv make(int d) {
+    FastDiv f;
+    f.d = (uint32_t)(d < 1 ? 1 : d);
+    f.mul = f.d == 1 ? 0u : (uint32_t)((0x100000000ull + f.d - 1) / f.d);
+    return f;
+  }
+};
+
 struct Gemm3Extra {
   int m_tiles, n_tiles;  // 128-row M tiles, BN-wide N tiles
   int acc_stride;        // TMEM column distance between accumulator stages
@@ -41,6 +57,7 @@ struct Gemm3Extra {
   int n_mma;             // MMA instructions along N per k-step (BN / n_mma columns each, <= 256)
   int ncols;             // output columns per tile (BN, or BN/2 for GEGLU)
   int log_rows_per_b;    // log2(bw*bh): tile row >> this = sample offset inside the tile
+  int log_bw;            // log2(bw) (tile shapes are powers of two)
   int nbufs;             // staging buffers in use (<= kG3MaxBufs)
   int vec_rows;          // rows of the per-tile epilogue vector staged in smem: samples a tile spans (time-embedding conv) or 1
   int vec_width;         // its width in floats (tile columns, rounded up to 32)
@@ -49,6 +66,7 @@ struct Gemm3Extra {
   float* partial;        // split-K: fp32 partial sums [splits][B*H*W][N] (the reduce kernel applies the epilogue)
   long long* prof;       // optional [gridDim.x][16] cycle counters per role (null: off); see gemm_host.cuh
   int debug;             // timing experiments only (results are garbage): 1 = skip the MMA instructions, 2 = skip the TMA loads
+  FastDiv d_ntiles, d_munits, d_tx, d_ty;  // divisors of the tile decode: n_tiles, ceil(m_tiles / CG), tiles_x, tiles_y
   int head_stride;       // > 0: output columns are heads of this many columns, tmOut is 5-D (make_epi_tmap_heads) and clips each head
 };
 
@@ -155,7 +173,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const uint32_t tmem_base = *tmem_slot_ptr;
   // split-K: unit u covers k-iterations [i0, i0 + n_it) of its tile
   auto k_range = [&](int u, int& i0, int& n_it) {
-    const int ks = (u / x.n_tiles) / m_units;
+    const int ks = x.d_munits.div(x.d_ntiles.div(u));
     i0 = ks * x.iters_split;
     n_it = iters - i0 < x.iters_split ? iters - i0 : x.iters_split;
   };
@@ -163,11 +181,15 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   // unit u -> this CTA's tile: n tile and the pixel box origin (out of range for the phantom tile of an odd pair)
   auto tile_coords = [&](int u, int& n_tile, int& x0, int& y0, int& b0) {
-    n_tile = u % x.n_tiles;
-    int mt = ((u / x.n_tiles) % m_units) * CG + (int)rank;
-    const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-    const int ty = mt % p.tiles_y; mt /= p.tiles_y;
-    x0 = tx * p.bw; y0 = ty * p.bh; b0 = mt * p.bn;
+    const int un = x.d_ntiles.div(u);
+    n_tile = u - un * x.n_tiles;
+    int mt = (un - x.d_munits.div(un) * m_units) * CG + (int)rank;
+    int q = x.d_tx.div(mt);
+    const int tx = mt - q * p.tiles_x;
+    mt = q;
+    q = x.d_ty.div(mt);
+    const int ty = mt - q * p.tiles_y;
+    x0 = tx * p.bw; y0 = ty * p.bh; b0 = q * p.bn;
   };
 
   if (warp == 0) {
@@ -190,8 +212,11 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int cx0 = x0 * p.stride - p.pad_x, cy0 = y0 * p.stride - p.pad_y;
         int i0, n_it;
         k_range(u, i0, n_it);
-        int tap = i0 / kchunks, kc = i0 - tap * kchunks;  // (two divisions per tile, none per iteration)
-        int r = tap / p.tap_w, sx = tap - r * p.tap_w;
+        int tap = 0, kc = 0, r = 0, sx = 0;  // (divisions only for a split-K range that starts inside the filter; none per iteration)
+        if (i0 != 0) {
+          tap = i0 / kchunks; kc = i0 - tap * kchunks;
+          r = tap / p.tap_w; sx = tap - r * p.tap_w;
+        }
         for (int it = 0; it < n_it; ++it) {
           const int cx = cx0 + sx, cy = cy0 + r;
           G3_TIMED(prof_on, w_empty, mbar_wait(eb, ph ^ 1u));
@@ -357,7 +382,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int u = unit0; u < total_units; u += unit_step, ++lt) {
       int n_tile, x0, y0, b0;
       tile_coords(u, n_tile, x0, y0, b0);
-      const int acc = lt % x.acc_bufs;
+      const int acc = x.acc_bufs == 2 ? (lt & 1) : 0;
       const uint32_t t_row = tmem_base + (uint32_t)(acc * x.acc_stride) + lane_off;
       const int g0 = lt * passes;                       // global index of this tile's pass 0
       const int ps0 = (g0 ^ set) & 1;                   // first pass of this tile that belongs to this set
@@ -369,7 +394,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       long long ln_m = -1;
       if (ln_apply || ln_out) {
         const int rr = row & (rpb - 1);
-        const int pb = b0 + (row >> x.log_rows_per_b), py = y0 + rr / p.bw, px = x0 + rr % p.bw;
+        const int pb = b0 + (row >> x.log_rows_per_b), py = y0 + (rr >> x.log_bw), px = x0 + (rr & (p.bw - 1));
         if (pb < p.B && py < p.H && px < p.W) ln_m = ((long long)pb * p.H + py) * p.W + px;
       }
       float ln_a = 1.f, ln_b = 0.f;
@@ -407,7 +432,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           pre[r] = a;
         }
       }
-      G3_TIMED(prof_on, w_tfull, mbar_wait(tfull_bar(acc), (uint32_t)(lt / x.acc_bufs) & 1u));
+      G3_TIMED(prof_on, w_tfull, mbar_wait(tfull_bar(acc), (uint32_t)(x.acc_bufs == 2 ? lt >> 1 : lt) & 1u));
       fence_after_sync();
       float* vtile = vec + (size_t)(lt & 1) * vrows * vwidth;
       if (has_vec) {
@@ -430,10 +455,10 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (partial_mode) {
         // split-K: raw fp32 accumulator rows -> partial[ks][pixel][column]; bias / time embedding / residual / bf16
         // rounding happen once, in splitk_reduce_kernel
-        const int ks = (u / x.n_tiles) / m_units;
+        const int ks = x.d_munits.div(x.d_ntiles.div(u));
         const int rpb = 1 << x.log_rows_per_b;
         const int rr = row & (rpb - 1);
-        const int pb = b0 + (row >> x.log_rows_per_b), py = y0 + rr / p.bw, px = x0 + rr % p.bw;
+        const int pb = b0 + (row >> x.log_rows_per_b), py = y0 + (rr >> x.log_bw), px = x0 + (rr & (p.bw - 1));
         const bool row_ok = pb < p.B && py < p.H && px < p.W;
         float* prow = x.partial + ((long long)ks * p.B * p.H * p.W + ((long long)pb * p.H + py) * p.W + px) * p.N +
                       (long long)n_tile * ncols;

@@ -373,6 +373,10 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       int lg = 0;
       while ((1 << lg) < p.bw * p.bh) ++lg;
       x.log_rows_per_b = lg;
+      int lbw = 0;
+      while ((1 << lbw) < p.bw) ++lbw;
+      SDTF_CHECK((1 << lbw) == p.bw, "gemm3: tile width must be a power of two");
+      x.log_bw = lbw;
       x.splits = split ? sk.splits : 1;
       x.iters_split = split ? sk.iters_split : iters;
       x.partial = split ? a.splitk_ws : nullptr;
@@ -393,6 +397,15 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       CUtensorMap tmA0 = make_act_tmap(a.a0, p.bw, p.bh, p.bn, a.stride);
       CUtensorMap tmA1 = a.a1.p ? make_act_tmap(a.a1, p.bw, p.bh, p.bn, a.stride) : tmA0;
       CUtensorMap tmB = make_weight_tmap(w.w, w.K, w.N, p.taps, p.BN / plan.n_mma / cg);
+      {
+        const long long m_units = (m_tiles + cg - 1) / cg, total = m_units * n_tiles * x.splits;
+        long long dmax = n_tiles > m_units ? n_tiles : m_units;
+        if (p.tiles_x > dmax) dmax = p.tiles_x;
+        if (p.tiles_y > dmax) dmax = p.tiles_y;
+        SDTF_CHECK((total + 2 * cg) * dmax < 0x100000000ll, "gemm3: tile count too large for the multiply-high tile decode");
+        x.d_ntiles = FastDiv::make(n_tiles); x.d_munits = FastDiv::make((int)m_units);
+        x.d_tx = FastDiv::make(p.tiles_x); x.d_ty = FastDiv::make(p.tiles_y);
+      }
       x.head_stride = 0;
       CUtensorMap tmOut;
       if (a.out_head_stride > 0) {

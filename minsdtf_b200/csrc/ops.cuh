@@ -57,6 +57,7 @@ struct GnScratch {
   unsigned* counters = nullptr; // [B], zero between launches (self-resetting)
   unsigned* gens = nullptr;     // [B], barrier generation (monotonic)
   float* stats = nullptr;       // [B][64]: mean, rstd per group (kept for debugging / tests)
+  int chains = 4;               // partial-sum chains per statistic (SDTF_GN_CHAINS=1: the round-1 single chain, for A/B)
   int share = 1;                // launches of this scratch may run next to (share - 1) other GroupNorm kernels: each gets
                                 // 1/share of the co-resident CTA slots (two spinning kernels must fit the device TOGETHER)
 };
@@ -72,6 +73,7 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, i
                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu, bf16* __restrict__ y, long long ldy) {
   extern __shared__ __align__(16) float gn_sm[];  // sums [lanes][C], then squares [lanes][C]
   __shared__ float s_stats[64];
+  __shared__ double s_chain[4][64];
   pdl_trigger();
   pdl_wait();  // x, and the barrier words of the previous GroupNorm
   const int vecs = C >> 3, gs = C >> 5;
@@ -169,11 +171,28 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, i
       __threadfence();
     }
     __syncthreads();
+    // every CTA of the sample adds the nblk partials — in a FIXED order (four interleaved chains of consecutive k, then the
+    // four chain sums in index order), so all CTAs get identical statistics and the result depends on nblk only.  Four
+    // chains with the loads issued ahead instead of one: a single chain was nblk dependent L2 round trips (64 x ~0.4 us
+    // in the small-batch class — most of the kernel's 32 us there).
+    if (threadIdx.x < 256) {  // (blockDim.x >= 256 for every channel count: launch_groupnorm)
+      const int pair = threadIdx.x & 63, chain = threadIdx.x >> 6;
+      const double* src = sc.partial + ((long long)b * kGnMaxBlk * 32) * 2 + pair;
+      const int per = sc.chains == 1 ? (chain == 0 ? nblk : 0) : (nblk + 3) >> 2, k0 = chain * per, k1 = min(nblk, k0 + per);
+      double acc = 0;
+      int k = k0;
+      for (; k + 4 <= k1; k += 4) {
+        const double v0 = __ldcg(src + (long long)k * 64), v1 = __ldcg(src + (long long)(k + 1) * 64);
+        const double v2 = __ldcg(src + (long long)(k + 2) * 64), v3 = __ldcg(src + (long long)(k + 3) * 64);
+        acc += v0; acc += v1; acc += v2; acc += v3;
+      }
+      for (; k < k1; ++k) acc += __ldcg(src + (long long)k * 64);
+      s_chain[chain][pair] = acc;
+    }
+    __syncthreads();
     if (threadIdx.x < 64) {
       const int g = threadIdx.x >> 1, w = threadIdx.x & 1;
-      double acc = 0;
-      const double* src = sc.partial + ((long long)b * kGnMaxBlk * 32 + g) * 2 + w;
-      for (int k = 0; k < nblk; ++k) acc += __ldcg(src + (long long)k * 64);
+      const double acc = ((s_chain[0][threadIdx.x] + s_chain[1][threadIdx.x]) + s_chain[2][threadIdx.x]) + s_chain[3][threadIdx.x];
       const double other = __shfl_xor_sync(0xffffffffu, acc, 1);
       const double S = w ? other : acc, Q = w ? acc : other;
       const double n = (double)HW * gs;
@@ -246,7 +265,7 @@ inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, 
   const long long HW = (long long)x.H * x.W;
   const int vecs = x.C / 8;
   int threads = (512 / vecs) * vecs;
-  SDTF_CHECK(threads >= vecs && threads <= 512, "GroupNorm: unsupported channel count");
+  SDTF_CHECK(threads >= vecs && threads <= 512 && threads >= 256, "GroupNorm: unsupported channel count");
   const int lanes = threads / vecs;
   const size_t smem = (size_t)lanes * x.C * 2 * sizeof(float);
   SDTF_CHECK(smem <= kGnMaxSmem, "GroupNorm: reduction scratch exceeds the shared-memory budget the occupancy was computed for");
@@ -281,6 +300,9 @@ inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, 
   if (by > x.B) by = x.B;
   SDTF_CHECK(by >= 1, "GroupNorm: a sample's CTAs do not fit on the device at once");
   dim3 grid((unsigned)nblk, (unsigned)by);
+  static const int chains_env = getenv("SDTF_GN_CHAINS") ? atoi(getenv("SDTF_GN_CHAINS")) : 4;
+  GnScratch scc = sc;
+  scc.chains = chains_env == 1 ? 1 : 4;
   // The per-sample barrier needs every CTA of the grid resident at once.  A COOPERATIVE launch makes that the driver's
   // promise instead of an assumption about what else runs on the device: if another stream / process / engine holds
   // SMs, the launch is refused (cudaErrorCooperativeLaunchTooLarge) or waits for room — it can no longer start with
@@ -293,10 +315,10 @@ inline int launch_groupnorm(cudaStream_t st, const View& x, const float* gamma, 
     attr[0].id = cudaLaunchAttributeCooperative;
     attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    SDTF_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const bf16*)x.p, (long long)x.ld, x.C, HW, (int)ppc, x.B, sc, gamma, beta,
+    SDTF_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_kernel, (const bf16*)x.p, (long long)x.ld, x.C, HW, (int)ppc, x.B, scc, gamma, beta,
                                  silu ? 1 : 0, y, ldy));
   } else {
-    launch_pdl(gn_fused_kernel, grid, dim3(threads), smem, st, 1, x.p, x.ld, x.C, HW, (int)ppc, x.B, sc, gamma, beta, silu ? 1 : 0, y, ldy);
+    launch_pdl(gn_fused_kernel, grid, dim3(threads), smem, st, 1, x.p, x.ld, x.C, HW, (int)ppc, x.B, scc, gamma, beta, silu ? 1 : 0, y, ldy);
   }
   SDTF_CUDA(cudaGetLastError());
   return 1;

@@ -38,6 +38,23 @@ def main():
     got = e.cfg_sched_step(eu, ec, x, StepCoef(7.5, 0.7, 0.9, 0.1, 0.0, 0, 0))
     assert np.isfinite(got).all()
     print("cfg_sched ok", flush=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "pipeline":
+        # a whole (tiny) job under the sanitizer: UNet (all four levels, folded upsamplers, folded LayerNorms, split-K),
+        # ControlNet + HintNet with in-epilogue injection, CFG step, VAE decode with the d = 512 flash attention
+        from minsdtf_b200 import synth
+        from minsdtf_b200.scheduler import Scheduler, timestep_embedding
+        e.load_state_dict(synth.make_state_dict("unet"), "unet")
+        e.load_state_dict(synth.make_controlnet_state_dict(), "controlnet")
+        e.load_state_dict(synth.make_state_dict("decoder"), "vae_decoder")
+        B, h = 1, 16
+        sch = Scheduler(active_tcd=False)
+        sch.set_timesteps(25)
+        ts = [int(t) for t in sch.timesteps[:2]]
+        img = e.denoise(synth.latents(B, h, h), synth.context(B), synth.uncond_context(B), np.stack([timestep_embedding(t) for t in ts]),
+                        sch.coefficients(ts, 7.5, 0.7), hint_image=(synth.edge_map(8 * h, 8 * h).astype(np.float32) / 255.0)[None],
+                        decode=True, use_cuda_graph=False)
+        assert img.shape == (B, 8 * h, 8 * h, 3)
+        print("pipeline (unet + controlnet + decode, 2 steps) ok", flush=True)
     e.close()
 
 
