@@ -410,7 +410,7 @@ def run_engine(args, rank, world, local_rank):
                          "flop_per_launch": conv["flop"] / conv["launches"], "ms_per_launch": conv["us"] / conv["launches"] / 1e3,
                          "ms_per_step_in_kernel": conv["us"] / 2 / 1e3,
                          "share_of_operator_time": conv["us"] / sum(v["us"] for v in tr_unet.values()),
-                         "how": "sdtf_trace_begin/end: eager launches on the engine's stream, CUDA events around every operator",
+                         "how": "sdtf_trace_begin/end: eager launches on the engine's stream, a CUDA event pair around every operator, read back after the step (the stream never drains between operators)",
                          "peak_source": peak_src},
             "roofline_best_shape": {"bound": "tensor", "achieved": conv_tflops, "peak": peak, "unit": "TFLOP/s", "frac": conv_tflops / peak,
                                     "traffic": ncu_traffic(conv_label), "kernel": conv_label,

@@ -106,6 +106,25 @@ struct TraceTotals {
   long long launches[4] = {0, 0, 0, 0};  // conv, attn, gn, ln
   double us[4] = {0, 0, 0, 0}, flop[4] = {0, 0, 0, 0}, bytes[4] = {0, 0, 0, 0};
   bool collecting = false, quiet = false;
+  // quiet collection (bench.py): the event pairs of all operators are only read back at sdtf_trace_end, so the stream never
+  // drains between operators — an operator's elapsed time is its kernel(s), not kernel + launch latency + host round trip
+  struct Pending { int kind; cudaEvent_t e0, e1; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get_event() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    SDTF_CUDA(cudaEventCreate(&e));
+    return e;
+  }
+  void drain() {  // caller has synchronised the stream
+    for (auto& pd : pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, pd.e0, pd.e1) == cudaSuccess) us[pd.kind] += ms * 1e3;
+      pool.push_back(pd.e0); pool.push_back(pd.e1);
+    }
+    pending.clear();
+  }
 };
 inline TraceTotals& trace_totals() {
   static TraceTotals t;
@@ -157,6 +176,17 @@ struct Ctx {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (!trace_on() || dry || (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)) {
       f();
+      return;
+    }
+    TraceTotals& tq = trace_totals();
+    if (tq.collecting && tq.quiet) {  // deferred read-back: no synchronisation between operators
+      const int k = kind[0] == 'c' ? 0 : kind[0] == 'a' ? 1 : kind[0] == 'g' ? 2 : 3;
+      TraceTotals::Pending pd{k, tq.get_event(), tq.get_event()};
+      SDTF_CUDA(cudaEventRecord(pd.e0, st));
+      f();
+      SDTF_CUDA(cudaEventRecord(pd.e1, st));
+      tq.pending.push_back(pd);
+      ++tq.launches[k]; tq.flop[k] += flop; tq.bytes[k] += bytes;
       return;
     }
     static cudaEvent_t e0 = nullptr, e1 = nullptr;

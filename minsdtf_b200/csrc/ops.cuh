@@ -191,7 +191,7 @@ gn_fused_kernel(const bf16* __restrict__ x, long long ld, int C, long long HW, i
     }
     __syncthreads();
     if (threadIdx.x < 64) {
-      const int g = threadIdx.x >> 1, w = threadIdx.x & 1;
+      const int w = threadIdx.x & 1;  // thread 2g + w holds statistic w (0: sum, 1: sum of squares) of group g
       const double acc = ((s_chain[0][threadIdx.x] + s_chain[1][threadIdx.x]) + s_chain[2][threadIdx.x]) + s_chain[3][threadIdx.x];
       const double other = __shfl_xor_sync(0xffffffffu, acc, 1);
       const double S = w ? other : acc, Q = w ? acc : other;

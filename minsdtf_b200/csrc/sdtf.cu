@@ -968,7 +968,8 @@ int sdtf_trace_begin(sdtf_engine* e) {
   SDTF_API_BEGIN
   SDTF_CUDA(cudaStreamSynchronize(e->st));
   TraceTotals& t = trace_totals();
-  t = TraceTotals();
+  t.drain();
+  for (int k = 0; k < 4; ++k) { t.launches[k] = 0; t.us[k] = t.flop[k] = t.bytes[k] = 0; }
   t.collecting = true;
   t.quiet = getenv("SDTF_TRACE") == nullptr;
   SDTF_API_END
@@ -979,6 +980,7 @@ int sdtf_trace_end(sdtf_engine* e, sdtf_trace_summary* out) {
   SDTF_CHECK(out != nullptr, "out is NULL");
   SDTF_CUDA(cudaStreamSynchronize(e->st));
   TraceTotals& t = trace_totals();
+  t.drain();
   for (int k = 0; k < 4; ++k) {
     out->launches[k] = t.launches[k]; out->us[k] = t.us[k]; out->flop[k] = t.flop[k]; out->bytes[k] = t.bytes[k];
   }
