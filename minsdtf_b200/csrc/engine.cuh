@@ -106,6 +106,7 @@ struct TraceTotals {
   long long launches[4] = {0, 0, 0, 0};  // conv, attn, gn, ln
   double us[4] = {0, 0, 0, 0}, flop[4] = {0, 0, 0, 0}, bytes[4] = {0, 0, 0, 0};
   bool collecting = false, quiet = false;
+  bool paused = false;  // set around work that is not part of what is being accounted (the once-per-job prologue of sdtf_denoise)
   // quiet collection (bench.py): the event pairs of all operators are only read back at sdtf_trace_end, so the stream never
   // drains between operators — an operator's elapsed time is its kernel(s), not kernel + launch latency + host round trip
   struct Pending { int kind; cudaEvent_t e0, e1; };
@@ -174,19 +175,25 @@ struct Ctx {
       ~Range() { if (on) nvtxRangePop(); }
     } range(nvtx_on() && !dry, kind, shape);
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (!trace_on() || dry || (cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone)) {
-      f();
-      return;
-    }
+    const bool capturing = cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
     TraceTotals& tq = trace_totals();
-    if (tq.collecting && tq.quiet) {  // deferred read-back: no synchronisation between operators
+    if (tq.collecting && tq.quiet && !dry && !tq.paused) {
+      // bench.py's accounting: one event pair per operator, read back after the job.  Under stream capture the records
+      // become EXTERNAL event-record nodes of the step graph, so the durations are those of the graph replay the bench
+      // times (eager launches of 20 us kernels are CPU-bound: their event intervals include launch gaps); every replay
+      // re-records the same events and the last one is read.
       const int k = kind[0] == 'c' ? 0 : kind[0] == 'a' ? 1 : kind[0] == 'g' ? 2 : 3;
       TraceTotals::Pending pd{k, tq.get_event(), tq.get_event()};
-      SDTF_CUDA(cudaEventRecord(pd.e0, st));
+      const unsigned flags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
+      SDTF_CUDA(cudaEventRecordWithFlags(pd.e0, st, flags));
       f();
-      SDTF_CUDA(cudaEventRecord(pd.e1, st));
+      SDTF_CUDA(cudaEventRecordWithFlags(pd.e1, st, flags));
       tq.pending.push_back(pd);
       ++tq.launches[k]; tq.flop[k] += flop; tq.bytes[k] += bytes;
+      return;
+    }
+    if (!trace_on() || dry || capturing || (tq.collecting && tq.quiet)) {
+      f();
       return;
     }
     static cudaEvent_t e0 = nullptr, e1 = nullptr;

@@ -720,9 +720,13 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
   const std::string key = std::to_string(B) + "x" + std::to_string(h) + "x" + std::to_string(w) + "x" + std::to_string(T) + "x" +
                           std::to_string(Tu) + (cfg ? (split ? (srank ? "S" : "s") : (two_pass ? "t" : "c")) : "-") +
                           (control ? "n" : "-") + (inpaint ? "m" : "-") + (d->step_noise ? "z" : "-") + "s" + std::to_string(S);
-  const bool use_graph = d->use_cuda_graph != 0 && !trace_on();  // per-operator events need eager launches
+  // SDTF_TRACE printing needs eager launches (a host read-back per operator); the quiet accounting of sdtf_trace_begin
+  // rides inside the captured graph as external event-record nodes
+  const bool accounting = trace_totals().collecting && trace_totals().quiet;
+  const bool use_graph = d->use_cuda_graph != 0 && (!trace_on() || accounting);
 
   e->run_sized([&](Ctx& c) {
+    trace_totals().paused = true;  // operator accounting (sdtf_trace_begin) covers the steps and the decode, not the once-per-job prologue
     // ---- job-resident buffers (same addresses for the same configuration => the captured graph stays valid) ----
     float* latent = c.ws->alloc_n<float>((size_t)B * n);
     bf16* lat8 = c.ws->alloc_n<bf16>((size_t)Bt * h * w * 8);
@@ -844,6 +848,7 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
       d->on_step(s + 1, d->on_step_user);
     };
 
+    trace_totals().paused = false;
     if (!c.dry) SDTF_CUDA(cudaEventRecord(e->ev[1], e->st));
     const size_t m_loop = c.ws->mark();
     if (c.dry) {
@@ -851,7 +856,7 @@ int sdtf_denoise(sdtf_engine* e, const sdtf_denoise_desc* d) {
     } else if (!use_graph) {
       for (int s = 0; s < S; ++s) { step(c); after_step(s); }
     } else {
-      const std::string gkey = key + "@" + std::to_string((uintptr_t)e->ws.base);
+      const std::string gkey = key + (accounting ? "#acct" : "") + "@" + std::to_string((uintptr_t)e->ws.base);
       if (!e->graph || e->graph_key != gkey) {
         e->drop_graph();
         Ctx gc = c;
