@@ -28,7 +28,9 @@ __device__ __forceinline__ float tanh_approx(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// barrier of ONE epilogue warp set (128 threads; ids 1 and 2): the two sets never wait for each other — a tile's passes
+// split 3 / 2 between them, and with a common barrier per tile the lighter set idled a pass per tile
+__device__ __forceinline__ void epi_set_bar_sync(int set) { asm volatile("bar.sync %0, 128;" ::"r"(1 + set) : "memory"); }
 __device__ __forceinline__ float gelu_tanh_fast(float g) {
   const float u = g * 0.7978845608f * (1.f + 0.044715f * g * g);
   return 0.5f * g * (1.f + tanh_approx(u));
@@ -121,7 +123,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   auto res_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + 4 + b); };
   auto stg_bar = [&](int b) { return bar_base + 8u * (2 * p.stages + 4 + kG3Bufs + b); };
   const uint32_t slot_off = bar_off + 8u * (2 * p.stages + 4 + 2 * kG3Bufs);
-  const uint32_t vec_off = slot_off + 16u;  // float [2][vec_rows][vec_width]: bias (+ time-embedding) of the current tile
+  const uint32_t vec_off = slot_off + 16u;  // float [2 sets][2][vec_rows][vec_width]: bias (+ time-embedding) of the current tile, one copy per epilogue warp set
   const uint32_t tmem_slot = smem_base + slot_off;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + slot_off);
 
@@ -377,7 +379,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int rpb = 1 << x.log_rows_per_b;
     const int vrows = x.vec_rows, vwidth = x.vec_width;
     const int Nvec = geglu ? p.N : Nout;
-    float* vec = reinterpret_cast<float*>(smem_gen + vec_off);
+    float* vec = reinterpret_cast<float*>(smem_gen + vec_off) + (size_t)set * 2 * x.vec_rows * x.vec_width;  // this set's double buffer
     int lt = 0;
     for (int u = unit0; u < total_units; u += unit_step, ++lt) {
       int n_tile, x0, y0, b0;
@@ -413,8 +415,8 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       // this tile's per-column vector (bias, + the time-embedding row of each sample the tile spans): fetched from
       // global BEFORE waiting for the accumulator so the latency hides behind the main loop, then staged in smem
       float4 pre[4];
-      const int vcol = 4 * et;
-      if (has_vec && et < 128 && vcol < vwidth) {
+      const int vcol = 4 * (et & 127);
+      if (has_vec && vcol < vwidth) {
         const int gcol = n_tile * (geglu ? p.BN : ncols) + vcol;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -436,12 +438,12 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       fence_after_sync();
       float* vtile = vec + (size_t)(lt & 1) * vrows * vwidth;
       if (has_vec) {
-        if (et < 128 && vcol < vwidth) {
+        if (vcol < vwidth) {
 #pragma unroll
           for (int r = 0; r < 4; ++r)
             if (r < vrows) *reinterpret_cast<float4*>(vtile + r * vwidth + vcol) = pre[r];
         }
-        epi_bar_sync();  // vector visible to all eight warps; also: everyone is done reading the tile before last's copy
+        epi_set_bar_sync(set);  // vector visible to the set's four warps; also: they are done reading the tile before last's copy
       }
       const float* vrow = vtile + vr * vwidth;
       if (ps0 >= passes) {  // no pass of this tile is ours: nothing to read from the accumulator

@@ -382,7 +382,7 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       x.partial = split ? a.splitk_ws : nullptr;
       x.vec_rows = a.ln_in ? 2 : ((a.temb && !split) ? p.bn : 1);
       x.vec_width = ((geglu ? p.BN : ncols) + 31) / 32 * 32;
-      const size_t vec_bytes = (size_t)2 * x.vec_rows * x.vec_width * 4;
+      const size_t vec_bytes = (size_t)2 * 2 * x.vec_rows * x.vec_width * 4;  // per epilogue warp set, double buffered
       const int cg = plan.cg;
       const size_t stage_bytes = kATileBytes + (size_t)(p.BN / cg) * 128;
       x.nbufs = (a.res && !split) ? kG3MaxBufs : 4;  // residual tiles are TMA-prefetched nbufs-1 passes ahead: latency needs depth

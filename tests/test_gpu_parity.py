@@ -330,6 +330,41 @@ def test_config1_full_size_25_steps_against_oracle(engine_unet, engine_vae, unet
     assert p_tf >= 30.0, p_tf
 
 
+def test_configs_3_4_5_full_size_free_running_against_oracle(engine_unet, engine_vae, engine_cnet, unet_sd, vae_sd, cnet_sd):
+    """BASELINE configs 3 (inpaint, covers img2img), 4 (ControlNet) and 5b (TCD) at the 512x512 size — step counts cut
+    (10 x 0.8 = 8, 3 and 4 steps) to keep the CPU oracle to about a minute; the loops run free (no teacher forcing)."""
+    B, h, H = 1, 64, 512
+    ctx, unc = synth.context(B), synth.uncond_context(B)
+    noise = synth.latents(B, h, h, seed=9)
+    weights = {"unet": unet_sd, "vae": vae_sd, "controlnet": cnet_sd}
+    sd = _pipeline(engine_unet, img_height=H, img_width=H)
+    sd.unconditional_context = unc[:1]
+    src, msk = synth.smooth_image(H, H), synth.center_mask(H, H)
+    in_arr, in_t = sd.preprocessed_image(src)
+    m_arr, m_lat = sd.preprocessed_mask(msk, 5)
+    ref = O.generate_image(weights, ctx, unc, noise, num_steps=10, guidance_scale=7.5, guidance_rescale=0.7,
+                           init_latent=O.vae_encode(vae_sd, in_t), strength=0.8, latent_mask=m_lat, input_image_array=in_arr,
+                           input_mask_array=m_arr, decode=False)
+    _, got = sd.generate_image(ctx, batch_size=B, num_steps=10, diffusion_noise=noise, guidance_rescale=0.7, reference_image=src,
+                               reference_image_strength=0.8, inpaint_mask=msk, mask_blur_strength=5, return_latent=True)
+    print(f"config 3 (inpaint 512x512, 8 steps) final latent rel err {rel(got, ref):.4g}")
+    assert rel(got, ref) <= 5e-2
+    edge = synth.edge_map(H, H)
+    hint_ref = O.hintnet_forward(cnet_sd, (edge.astype(np.float32) / 255.0)[None])
+    ref = O.generate_image(weights, ctx, unc, noise, num_steps=3, guidance_scale=7.5, guidance_rescale=0.0, hint=hint_ref, decode=False)
+    _, got = sd.generate_image(ctx, batch_size=B, num_steps=3, diffusion_noise=noise, control_net_image=edge, return_latent=True)
+    print(f"config 4 (ControlNet 512x512, 3 steps) final latent rel err {rel(got, ref):.4g}")
+    assert rel(got, ref) <= 5e-2
+    sd_t = _pipeline(engine_unet, img_height=H, img_width=H, active_tcd=True)
+    np.random.seed(123456)
+    ref = O.generate_image(weights, ctx, None, noise, num_steps=4, guidance_scale=0.0, active_tcd=True, decode=False)
+    np.random.seed(123456)
+    _, got = sd_t.generate_image(ctx, batch_size=B, num_steps=4, diffusion_noise=noise, unconditional_guidance_scale=0.0,
+                                 return_latent=True)
+    print(f"config 5b (TCD 512x512, 4 steps) final latent rel err {rel(got, ref):.4g}")
+    assert rel(got, ref) <= 5e-2
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # the three public entry points themselves (stable_diffusion.py:84-174), token-id prompts through the engine's text tower
 # ----------------------------------------------------------------------------------------------------------------
