@@ -616,6 +616,10 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 // O = (O_a 2^(m_a-m) + O_b 2^(m_b-m)) / (l_a 2^(m_a-m) + l_b 2^(m_b-m)).
 // Warps 0-15 softmax (quad = w&3, query tile g = (w>>2)&1, half h = w>>3), 16/17 MMA issue of tile 0/1, 18 TMA.
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+}
+static constexpr int kCtlRegs = 40, kSmxRegs = 104;  // setmaxnreg split of 640 x 96 registers (A/B: SDTF_ATTN_SETREG)
 static constexpr int kAHThreads = 640;  // 16 softmax warps + one control warpgroup (MMA x2, TMA, idle)
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -627,7 +631,7 @@ __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 2, 5
 // registers BEFORE waiting for P V_{j-1} (the wait only guards the P buffer and the rare O rescale).
 // PP16: score pairs out of every 8 (16 keys) whose exponentials run on the FMA pipe instead of MUFU.EX2 (2 = a quarter,
 // 3 = three eighths, 4 = half); 0 selects the round-1 scalar code (2 of 8 scalar polynomials) for A/B runs.
-template <int KS, int DV, int DEFER, int PP16>
+template <int KS, int DV, int DEFER, int PP16, bool SETREG = false>
 __global__ void __launch_bounds__(kAHThreads, 1)
 attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -694,6 +698,7 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
   if (warp == 18) {
     // ===== TMA producer =====
+    if (SETREG) setmaxnreg_dec<kCtlRegs>();
     if (elect_one()) {
       mbar_expect_tx(q_full, 2 * kChunk);
       tma_load_4d(sQ, &tmQ, q_full, 0, head, q0, b);
@@ -711,6 +716,7 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     __syncwarp();
   } else if (warp == 16 || warp == 17) {
     // ===== MMA issuer of query tile g = warp - 16 =====
+    if (SETREG) setmaxnreg_dec<kCtlRegs>();
     if (elect_one()) {
       const int g = warp - 16;
       const uint32_t tS = tmem + 128u * g;
@@ -759,6 +765,7 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   } else if (warp == 19) {
     // ===== ones column: V[:, d] = 1 in every landed V tile, so that P V also produces the softmax denominator
     // (column d of O = sum_k P[q,k]) on the tensor core instead of one FADD per exponential in the softmax warps
+    if (SETREG) setmaxnreg_dec<kCtlRegs>();
     const uint32_t chunk = (uint32_t)(p.d * 2) >> 4, within = (uint32_t)(p.d * 2) & 15u;
     for (int j = 0; j < nkv; ++j) {
       const int vs = j % VST;
@@ -773,6 +780,7 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
   } else if (warp < 16) {
     // ===== softmax: thread = (query row, key half) =====
+    if (SETREG) setmaxnreg_inc<kSmxRegs>();
     const int g = (warp >> 2) & 1, h = warp >> 3;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -780,6 +788,9 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t tO = tmem + 256u + (uint32_t)(DV * (2 * g + h)) + lane_off;
     uint8_t* rowp = gen + (sP - base) + (uint32_t)(2 * g + h) * kChunk + row * 128;
     const int sw = row & 7;
+    // 16-byte chunk c of this thread's P row sits at prow ^ (c << 4) (128-byte swizzle; bits 4-6 of the row start are 0)
+    uint32_t prow = (sP + (uint32_t)(2 * g + h) * kChunk + (uint32_t)row * 128u) | ((uint32_t)sw << 4);
+    if (SETREG) asm volatile("" : "+r"(prow));  // keep it in a register: ptxas otherwise recomputes it from %tid every tile
     float m_run = -INFINITY;  // (the running denominator lives in column d of the accumulator)
     for (int j = 0; j < nkv; ++j) {
       int nvalid = p.Nk - j * 128 - 64 * h;  // valid keys of this half
@@ -875,10 +886,17 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
         fence_after_sync();
       }
+      if (SETREG) {
 #pragma unroll
-      for (int c = 0; c < DEFER; c += 8) *reinterpret_cast<uint4*>(rowp + (((c >> 3) ^ sw) << 4)) = early[c >> 3];
+        for (int c = 0; c < DEFER; c += 8) st_shared_v4(prow ^ (uint32_t)(c << 1), early[c >> 3]);
 #pragma unroll
-      for (int c = DEFER; c < 64; c += 8) *reinterpret_cast<uint4*>(rowp + (((c >> 3) ^ sw) << 4)) = exp8(c);
+        for (int c = DEFER; c < 64; c += 8) st_shared_v4(prow ^ (uint32_t)(c << 1), exp8(c));
+      } else {
+#pragma unroll
+        for (int c = 0; c < DEFER; c += 8) *reinterpret_cast<uint4*>(rowp + (((c >> 3) ^ sw) << 4)) = early[c >> 3];
+#pragma unroll
+        for (int c = DEFER; c < 64; c += 8) *reinterpret_cast<uint4*>(rowp + (((c >> 3) ^ sw) << 4)) = exp8(c);
+      }
       fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
       fence_before_sync();
       __syncwarp();
@@ -946,6 +964,333 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 }
 
 constexpr size_t attn2h_smem_bytes() { return 1024 + (size_t)(2 + 3 + 3 + 4) * 128 * 128 + 2048 + 8 + 8 * 12 + 96 + 8 * 3 + 16 + 16; }
+
+// ------------------------------------------------------------------------------------------------------
+// attn2x: the half-row design of attn2h for d = 80 (the 32x32 level).  Four accumulators of 96 columns (80 + the ones
+// column, rounded to the MMA granularity) leave 128 TMEM columns for S, so the two query tiles SHARE one S buffer: a
+// thread pulls its 64 scores into registers as soon as they exist, tile g's Q K^T is issued when the other tile's
+// threads have pulled theirs, and the two tiles settle half a key tile apart.  K / V rows are two 64-column chunks;
+// K is double-buffered, V single (P V_j needs V_j a softmax pass after Q K^T_j needed K_j), each ring with its own
+// producer so that K_{j+1} is not held back behind the wait for V_j's slot.
+// Warps 0-15 softmax (quad = w&3, query tile g = (w>>2)&1, half h = w>>3), 16/17 MMA issue of tile 0/1, 18 TMA of Q and K,
+// 19 TMA of V + the ones column.
+// ------------------------------------------------------------------------------------------------------
+template <int KS, int DV, int PP16>
+__global__ void __launch_bounds__(kAHThreads, 1)
+attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using namespace tc05;
+  extern __shared__ uint8_t smem_raw[];
+  constexpr uint32_t kChunk = 128 * 128;  // [128 rows][64 bf16] swizzled = 16 KB
+  constexpr int DCH = 2, KST = 2;
+  constexpr uint32_t kTmemCols = 512;
+  static_assert(128 + 4 * DV <= 512 && DV % 16 == 0 && DV <= 128, "S (128 columns) and four accumulators must fit TMEM");
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;                          // 2 tiles x DCH chunks
+  const uint32_t sK = sQ + 2 * DCH * kChunk;         // KST x DCH chunks
+  const uint32_t sV = sK + KST * DCH * kChunk;       // DCH chunks
+  const uint32_t sP = sV + DCH * kChunk;             // chunk 2g+h = P of query tile g, key half h
+  // (the running maxima of the h = 1 threads cross to their h = 0 partners through the head of tile g's own Q chunks,
+  //  which nothing reads after that tile's last Q K^T)
+  const uint32_t bars = sP + 4 * kChunk;
+  const uint32_t q_full = bars;
+  auto k_full = [&](int s) { return bars + 8u + 8u * s; };
+  auto k_empty = [&](int s) { return bars + 24u + 8u * s; };
+  const uint32_t v_full = bars + 40u, v_empty = bars + 48u, v_ones = bars + 56u;
+  const uint32_t gbars = bars + 64u;
+  auto s_full = [&](int g) { return gbars + 8u * g; };
+  auto s_taken = [&](int g) { return gbars + 16u + 8u * g; };
+  auto p_full = [&](int g, int h) { return gbars + 32u + 8u * (2 * g + h); };
+  auto o_done = [&](int g, int h) { return gbars + 64u + 8u * (2 * g + h); };
+  const uint32_t tmem_slot = gbars + 96u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
+  const int nkv = (p.Nk + 127) / 128;
+
+  pdl_trigger();
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 2); }  // released by both tiles' MMA warps
+    mbar_init(v_full, 1); mbar_init(v_empty, 2); mbar_init(v_ones, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(s_full(g), 1);
+      mbar_init(s_taken(g), 8);  // one arrive per softmax warp of the tile (both halves)
+      for (int h = 0; h < 2; ++h) { mbar_init(p_full(g, h), 4); mbar_init(o_done(g, h), 1); }
+    }
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc(tmem_slot, kTmemCols);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = *tmem_slot_ptr;
+  pdl_wait();  // Q / K / V come from the projection GEMMs
+
+  auto keys_in_tile = [&](int j) {  // valid keys of tile j rounded up to the MMA granularity
+    int n = p.Nk - j * 128;
+    n = n > 128 ? 128 : n;
+    return (n + 15) & ~15;
+  };
+
+  if (warp == 18) {
+    // ===== TMA producer of Q and K =====
+    setmaxnreg_dec<kCtlRegs>();
+    if (elect_one()) {
+      mbar_expect_tx(q_full, 2 * DCH * kChunk);
+#pragma unroll
+      for (int c = 0; c < DCH; ++c) {
+        tma_load_4d(sQ + c * kChunk, &tmQ, q_full, 64 * c, head, q0, b);
+        tma_load_4d(sQ + (DCH + c) * kChunk, &tmQ, q_full, 64 * c, head, q0 + 128, b);
+      }
+      for (int j = 0; j < nkv; ++j) {
+        const int ks = j % KST;
+        mbar_wait(k_empty(ks), ((uint32_t)(j / KST) & 1u) ^ 1u);
+        mbar_expect_tx(k_full(ks), DCH * kChunk);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sK + (ks * DCH + c) * kChunk, &tmK, k_full(ks), 64 * c, head, j * 128, b);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 16 || warp == 17) {
+    // ===== MMA issuer of query tile g = warp - 16 =====
+    setmaxnreg_dec<kCtlRegs>();
+    if (elect_one()) {
+      const int g = warp - 16;
+      const uint32_t tS = tmem;  // shared by the two tiles
+      const uint64_t dq = make_smem_desc_sw128(sQ + g * DCH * kChunk, 16, 1024);
+      auto issue_qk = [&](int j) {
+        const int st = j % KST;
+        mbar_wait(k_full(st), (uint32_t)(j / KST) & 1u);
+        // the S buffer is free once the OTHER tile's threads have pulled their scores: tile 1's S_{j-1} before tile 0's
+        // S_j, tile 0's S_j before tile 1's S_j
+        if (g == 0) { if (j > 0) mbar_wait(s_taken(1), (uint32_t)(j - 1) & 1u); }
+        else mbar_wait(s_taken(0), (uint32_t)j & 1u);
+        fence_after_sync();
+        const uint32_t idesc = make_idesc_bf16(128, keys_in_tile(j), 0, 0);
+        const uint64_t dk = make_smem_desc_sw128(sK + st * DCH * kChunk, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {  // k-step k: chunk k / 4, 32 bytes per step inside the 128-byte swizzled row
+          const uint64_t off = (uint64_t)((k >> 2) * (kChunk >> 4) + (k & 3) * 2);
+          mma_f16_ss(tS, dq + off, dk + off, idesc, k != 0);
+        }
+        mma_commit(s_full(g));
+        mma_commit(k_empty(st));
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      const uint32_t idesc_pv = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
+      for (int j = 0; j < nkv; ++j) {
+        if (j + 1 < nkv) issue_qk(j + 1);
+        mbar_wait(v_ones, (uint32_t)j & 1u);  // V tile landed and its ones column is in place
+        fence_after_sync();
+        const int ksteps = keys_in_tile(j) >> 4;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(p_full(g, h), (uint32_t)j & 1u);  // this half of P_j is in shared memory
+          fence_after_sync();
+          const uint32_t tO = tmem + 128u + (uint32_t)(DV * (2 * g + h));
+          const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * g + h) * kChunk, 16, 1024);
+          for (int k = 4 * h; k < 4 * h + 4 && k < ksteps; ++k) {
+            const uint64_t db = make_smem_desc_sw128(sV + (uint32_t)k * 2048u, kChunk, 1024);
+            mma_f16_ss(tO, dp + 2 * (k & 3), db, idesc_pv, (j > 0) || (k > 4 * h));
+          }
+          mma_commit(o_done(g, h));
+        }
+        mma_commit(v_empty);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 19) {
+    // ===== V producer + ones column: V[:, d] = 1 in every landed V tile, so that P V also produces the softmax
+    // denominator (column d of O = sum_k P[q,k]) on the tensor core =====
+    setmaxnreg_dec<kCtlRegs>();
+    const uint32_t c64 = (uint32_t)p.d >> 6, chunk = ((uint32_t)(p.d & 63) * 2) >> 4, within = (uint32_t)(p.d * 2) & 15u;
+    for (int j = 0; j < nkv; ++j) {
+      if (lane == 0) {
+        if (j > 0) mbar_wait(v_empty, (uint32_t)(j - 1) & 1u);  // P V_{j-1} of both query tiles has completed
+        mbar_expect_tx(v_full, DCH * kChunk);
+#pragma unroll
+        for (int c = 0; c < DCH; ++c) tma_load_4d(sV + c * kChunk, &tmV, v_full, 64 * c, head, j * 128, b);
+      }
+      __syncwarp();
+      mbar_wait(v_full, (uint32_t)j & 1u);
+      uint8_t* vt = gen + (sV - base) + c64 * kChunk;
+#pragma unroll
+      for (int r = lane; r < 128; r += 32)
+        *reinterpret_cast<uint16_t*>(vt + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4) + within) = 0x3F80;  // bf16 1.0
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_ones);
+    }
+  } else if (warp < 16) {
+    // ===== softmax: thread = (query row, key half) =====
+    setmaxnreg_inc<kSmxRegs>();
+    const int g = (warp >> 2) & 1, h = warp >> 3;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem + 64u * h + lane_off;
+    const uint32_t tO = tmem + 128u + (uint32_t)(DV * (2 * g + h)) + lane_off;
+    const int sw = row & 7;
+    // 16-byte chunk c of this thread's P row sits at prow ^ (c << 4) (128-byte swizzle; bits 4-6 of the row start are 0)
+    uint32_t prow = (sP + (uint32_t)(2 * g + h) * kChunk + (uint32_t)row * 128u) | ((uint32_t)sw << 4);
+    asm volatile("" : "+r"(prow));  // keep it in a register: ptxas otherwise recomputes it from %tid every tile
+    float m_run = -INFINITY;  // (the running denominator lives in column d of the accumulator)
+    for (int j = 0; j < nkv; ++j) {
+      int nvalid = p.Nk - j * 128 - 64 * h;  // valid keys of this half
+      nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
+      mbar_wait(s_full(g), (uint32_t)j & 1u);
+      fence_after_sync();
+      uint32_t sv[64];
+      tmem_ld32_at<0>(tS, sv);
+      tmem_ld32_at<32>(tS + 32, sv);
+      tmem_ld_wait();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_taken(g));
+      if (nvalid < 64) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i)
+          if (i >= nvalid) sv[i] = 0xff800000u;  // -inf
+      }
+      float mx = fmax3(__uint_as_float(sv[0]), __uint_as_float(sv[1]), __uint_as_float(sv[2]));
+      float mx2 = fmax3(__uint_as_float(sv[3]), __uint_as_float(sv[4]), __uint_as_float(sv[5]));
+#pragma unroll
+      for (int i = 6; i + 3 < 64; i += 4) {
+        mx = fmax3(mx, __uint_as_float(sv[i]), __uint_as_float(sv[i + 1]));
+        mx2 = fmax3(mx2, __uint_as_float(sv[i + 2]), __uint_as_float(sv[i + 3]));
+      }
+      mx = fmax3(mx, mx2, fmaxf(__uint_as_float(sv[62]), __uint_as_float(sv[63])));
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);
+      const bool grow = (m_new - m_run) > 8.f;  // (-inf) - (-inf) = NaN -> false: nothing to move
+      bool waited = (j == 0);  // P V_{j-1} of this half must be complete before O is touched or P overwritten
+      if (__any_sync(0xffffffffu, grow)) {
+        if (!waited) {
+          mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+          fence_after_sync();
+          waited = true;
+        }
+        const float alpha = grow ? ex2f(m_run - m_new) : 1.f;
+        if (grow) m_run = m_new;
+        if (j > 0) {
+#pragma unroll
+          for (int c = 0; c < DV; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(tO + c, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st16(tO + c, v);
+          }
+          tmem_st_wait();
+        }
+      }
+      const float neg_m = (m_run == -INFINITY) ? 0.f : -m_run;  // no valid key yet: every term below becomes 2^-inf = 0
+      const f32x2 scale2 = pack2(p.scale_log2, p.scale_log2), negm2 = pack2(neg_m, neg_m);
+      auto exp8 = [&](int c) {
+        float e[8];
+        // pairs on the FMA pipe in this block of 8 keys: PP16 / 2, the odd one going to the odd blocks
+        const int npoly = (PP16 >> 1) + ((PP16 & 1) & (c >> 3));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const f32x2 x2 = fma2(pack2(__uint_as_float(sv[c + 2 * j]), __uint_as_float(sv[c + 2 * j + 1])), scale2, negm2);
+          if (j >= 4 - npoly) {
+            ex2_poly2(x2, e[2 * j], e[2 * j + 1]);
+          } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            e[2 * j] = ex2f(x0);
+            e[2 * j + 1] = ex2f(x1);
+          }
+        }
+        uint4 w;
+        w.x = pack_bf16(e[0], e[1]); w.y = pack_bf16(e[2], e[3]);
+        w.z = pack_bf16(e[4], e[5]); w.w = pack_bf16(e[6], e[7]);
+        return w;
+      };
+      uint4 early[2];
+      early[0] = exp8(0);
+      early[1] = exp8(8);
+      if (!waited) {
+        mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+        fence_after_sync();
+      }
+      st_shared_v4(prow, early[0]);
+      st_shared_v4(prow ^ 16u, early[1]);
+#pragma unroll
+      for (int c = 16; c < 64; c += 8) st_shared_v4(prow ^ (uint32_t)(c << 1), exp8(c));
+      fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(g, h));
+    }
+    // ---- merge the two halves of each row and write O / l as bf16 ----
+    float* xch = reinterpret_cast<float*>(gen + (sQ - base) + (uint32_t)(g * DCH) * kChunk);
+    if (h == 1) xch[row] = m_run;
+    softmax_bar_sync();
+    if (h == 0) {
+      mbar_wait(o_done(g, 0), (uint32_t)(nkv - 1) & 1u);
+      mbar_wait(o_done(g, 1), (uint32_t)(nkv - 1) & 1u);
+      fence_after_sync();
+      const float m_other = xch[row];
+      const float m_all = fmaxf(m_run, m_other);
+      const float fa = (m_run == -INFINITY) ? 0.f : ex2f(m_run - m_all);
+      const float fb = (m_other == -INFINITY) ? 0.f : ex2f(m_other - m_all);
+      const uint32_t tOb = tO + (uint32_t)DV;  // accumulator of the other half (same TMEM lanes)
+      float la, lb;  // denominators: column d of each accumulator
+      {
+        uint32_t va[16], vb[16];
+        const int cl = p.d & ~15;
+        tmem_ld16(tO + cl, va);
+        tmem_ld16(tOb + cl, vb);
+        tmem_ld_wait();
+        la = 0.f; lb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (i == (p.d & 15)) { la = __uint_as_float(va[i]); lb = __uint_as_float(vb[i]); }
+      }
+      const float inv_l = 1.f / ((fa != 0.f ? la * fa : 0.f) + (fb != 0.f ? lb * fb : 0.f));
+      const float ca = fa * inv_l, cb = fb * inv_l;
+      const int q = q0 + g * 128 + row;
+      const bool ok = q < p.Nq;
+      bf16* orow = p.out + ((long long)b * p.Nq + q) * p.ldo + head * p.d;
+#pragma unroll
+      for (int c = 0; c < DV; c += 16) {
+        uint32_t va[16], vb[16];
+        tmem_ld16(tO + c, va);
+        tmem_ld16(tOb + c, vb);
+        tmem_ld_wait();
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float xa = fa != 0.f ? __uint_as_float(va[i]) : 0.f;  // an accumulator that never saw a key is uninitialised
+          const float xb = fb != 0.f ? __uint_as_float(vb[i]) : 0.f;
+          o[i] = xa * ca + xb * cb;
+        }
+        if (ok) {
+          uint4 w0, w1;
+          w0.x = pack_bf16(o[0], o[1]);   w0.y = pack_bf16(o[2], o[3]);
+          w0.z = pack_bf16(o[4], o[5]);   w0.w = pack_bf16(o[6], o[7]);
+          w1.x = pack_bf16(o[8], o[9]);   w1.y = pack_bf16(o[10], o[11]);
+          w1.z = pack_bf16(o[12], o[13]); w1.w = pack_bf16(o[14], o[15]);
+          if (c + 8 <= p.d) *reinterpret_cast<uint4*>(orow + c) = w0;
+          if (c + 16 <= p.d) *reinterpret_cast<uint4*>(orow + c + 8) = w1;
+        }
+        __syncwarp();
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem, kTmemCols);
+}
+
+constexpr size_t attn2x_smem_bytes() { return 1024 + (size_t)(4 + 4 + 2 + 4) * 128 * 128 + 64 + 96 + 16 + 16; }
+
+
 
 template <int DCH, int KST, int VST>
 constexpr size_t attn2q_smem_bytes() {
@@ -1487,11 +1832,9 @@ inline void init_attn_kernels() {
   static_assert(attn2q_smem_bytes<2, 2, 1>() <= 232448, "d = 80 two-tile attention must fit 227 KB of shared memory");
   SDTF_CUDA(cudaFuncSetAttribute(attn2q_kernel<2, 5, 80, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)attn2q_smem_bytes<2, 2, 1>()));
-  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
-  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
   SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
-  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
-  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2x_kernel<5, 96, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2x_smem_bytes()));
   init_attn_t<2, 5, 80, 2, 2>();
   init_attn_t<3, 10, 160, 1, 1>();
   SDTF_CUDA(cudaFuncSetAttribute(vattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vattn_smem_bytes()));
@@ -1555,15 +1898,13 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
       static const int use_2q = getenv("SDTF_ATTN_2Q") ? atoi(getenv("SDTF_ATTN_2Q")) : 0;  // A/B: previous full-row kernel
       if (!use_2q) {
         SDTF_CHECK(a.d < 48, "attn2h keeps the softmax denominator in accumulator column d: needs d < DV");
-        // SDTF_ATTN_PP16 (A/B): exponential pairs per 16 keys on the FMA pipe — 0: round-1 scalar code, 2 / 3 / 4 packed;
-        // SDTF_ATTN_DEFER (round 1: 0.735 / 0.724 / 0.756 ms for 0 / 16 / 32): 0 or 16
-        static const int defer = getenv("SDTF_ATTN_DEFER") ? atoi(getenv("SDTF_ATTN_DEFER")) : 16;
-        static const int pp16 = getenv("SDTF_ATTN_PP16") ? atoi(getenv("SDTF_ATTN_PP16")) : 3;
+        // SDTF_ATTN_SETREG=0 (A/B): the kernel without the per-role register budget and the direct P stores.
+        // Tuning history of the two other knobs: 3 of every 8 exponential pairs on the FMA pipe (0.725 / 0.749 / 0.702 /
+        // 0.754 ms for scalar code, 2, 3, 4 of 8) and the first 16 keys' exponentials before the wait for P V_{j-1}
+        // (0.674 / 0.665 / 0.693 ms for 0 / 16 / 32), profiles/r02_b_attn2h_packed_exp.log, r02_u_attn_ab.log.
+        static const int setreg = getenv("SDTF_ATTN_SETREG") ? atoi(getenv("SDTF_ATTN_SETREG")) : 1;
         const size_t sm = attn2h_smem_bytes();
-        if (defer == 0) launch_pdl(attn2h_kernel<3, 48, 0, 3>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
-        else if (pp16 == 0) launch_pdl(attn2h_kernel<3, 48, 16, 0>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
-        else if (pp16 == 2) launch_pdl(attn2h_kernel<3, 48, 16, 2>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
-        else if (pp16 == 4) launch_pdl(attn2h_kernel<3, 48, 16, 4>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
+        if (setreg) launch_pdl(attn2h_kernel<3, 48, 16, 3, true>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
         else launch_pdl(attn2h_kernel<3, 48, 16, 3>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
         SDTF_CUDA(cudaGetLastError());
         return;
@@ -1587,7 +1928,9 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
       launch_attn_t<2, 5, 80, 2, 2>(stream, a, p, tq, tk, tv);
     } else {  // two query tiles per CTA, warp-specialised (softmax of one tile overlaps the MMAs of the other)
       dim3 grid((unsigned)ceil_div(a.Nq, 256), (unsigned)a.heads, (unsigned)a.B);
-      launch_pdl(attn2q_kernel<2, 5, 80, 2, 1>, grid, dim3(kA2Threads), attn2q_smem_bytes<2, 2, 1>(), stream, 1, tq, tk, tv, p);
+      static const int use_2x = getenv("SDTF_ATTN_2X") ? atoi(getenv("SDTF_ATTN_2X")) : 1;  // A/B: 0 = full-row kernel (round 1)
+      if (use_2x) launch_pdl(attn2x_kernel<5, 96, 3>, grid, dim3(kAHThreads), attn2x_smem_bytes(), stream, 1, tq, tk, tv, p);
+      else launch_pdl(attn2q_kernel<2, 5, 80, 2, 1>, grid, dim3(kA2Threads), attn2q_smem_bytes<2, 2, 1>(), stream, 1, tq, tk, tv, p);
     }
   } else if (a.d == 160) {
     launch_attn_t<3, 10, 160, 1, 1>(stream, a, p, tq, tk, tv);
