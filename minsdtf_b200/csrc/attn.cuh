@@ -616,10 +616,17 @@ attn2q_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 // O = (O_a 2^(m_a-m) + O_b 2^(m_b-m)) / (l_a 2^(m_a-m) + l_b 2^(m_b-m)).
 // Warps 0-15 softmax (quad = w&3, query tile g = (w>>2)&1, half h = w>>3), 16/17 MMA issue of tile 0/1, 18 TMA.
 // ------------------------------------------------------------------------------------------------------
+// A value that must stay in its register: routed through a shuffle with the thread's own lane, which ptxas will not
+// re-derive (an empty asm with a "+r" operand is transparent to it: it went on rebuilding the addresses from %tid).
+__device__ __forceinline__ void pin_reg(uint32_t& x, int lane) { x = __shfl_sync(0xffffffffu, x, lane); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& w) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
 }
-static constexpr int kCtlRegs = 40, kSmxRegs = 104;  // setmaxnreg split of 640 x 96 registers (A/B: SDTF_ATTN_SETREG)
+#ifndef SDTF_ATTN_SMX_REGS
+#define SDTF_ATTN_SMX_REGS 112
+#define SDTF_ATTN_CTL_REGS 32
+#endif
+static constexpr int kCtlRegs = SDTF_ATTN_CTL_REGS, kSmxRegs = SDTF_ATTN_SMX_REGS;  // setmaxnreg split of 640 x 96 registers (A/B: SDTF_ATTN_SETREG)
 static constexpr int kAHThreads = 640;  // 16 softmax warps + one control warpgroup (MMA x2, TMA, idle)
 template <int N>
 __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -692,9 +699,11 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     return (n + 15) & ~15;
   };
 
-  // register budget: the kernel is compiled for 96 registers per thread (640 x 96 = 60 K); the control warpgroup hands
-  // most of its share back so that the softmax warpgroups can hold a 64-wide S row without spilling
-  // (setmaxnreg: ptxas refuses to allocate this kernel under a per-warpgroup budget)
+  // register budget: the kernel is launched with 96 registers per thread (640 x 96 = 60 K).  With SETREG every role branch
+  // starts with setmaxnreg: the control warpgroup keeps 32 registers, the four softmax warpgroups take 112 — enough for a
+  // 64-wide S row, 32 packed results in flight and the loop-invariant addresses without spills (0.698 -> 0.617 ms at
+  // 64x64 together with the pinned addresses and the direct P stores).  The instruction must sit INSIDE each branch: placed
+  // before the role dispatch ptxas allocates the whole kernel under the smaller of the two budgets.
 
   if (warp == 18) {
     // ===== TMA producer =====
@@ -790,20 +799,26 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int sw = row & 7;
     // 16-byte chunk c of this thread's P row sits at prow ^ (c << 4) (128-byte swizzle; bits 4-6 of the row start are 0)
     uint32_t prow = (sP + (uint32_t)(2 * g + h) * kChunk + (uint32_t)row * 128u) | ((uint32_t)sw << 4);
-    if (SETREG) asm volatile("" : "+r"(prow));  // keep it in a register: ptxas otherwise recomputes it from %tid every tile
     float m_run = -INFINITY;  // (the running denominator lives in column d of the accumulator)
+    // loop-invariant addresses, pinned: ptxas otherwise rebuilds each of them from %tid and the shared window every tile
+    uint32_t b_sfull = s_full(g), b_staken = s_empty(g), b_pfull = p_full(g, h), b_odone = o_done(g, h), tSp = tS;
+    int last_valid = p.Nk - (nkv - 1) * 128 - 64 * h;  // valid keys of this half in the last tile (all others are full)
+    last_valid = last_valid < 0 ? 0 : (last_valid > 64 ? 64 : last_valid);
+    if (SETREG) {
+      pin_reg(b_sfull, lane); pin_reg(b_staken, lane); pin_reg(b_pfull, lane); pin_reg(b_odone, lane); pin_reg(tSp, lane);
+      pin_reg(prow, lane);
+    }
     for (int j = 0; j < nkv; ++j) {
-      int nvalid = p.Nk - j * 128 - 64 * h;  // valid keys of this half
-      nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
-      mbar_wait(s_full(g), (uint32_t)j & 1u);
+      const int nvalid = (j == nkv - 1) ? last_valid : 64;
+      mbar_wait(b_sfull, (uint32_t)j & 1u);
       fence_after_sync();
       uint32_t sv[64];
-      tmem_ld32_at<0>(tS, sv);
-      tmem_ld32_at<32>(tS + 32, sv);
+      tmem_ld32_at<0>(tSp, sv);
+      tmem_ld32_at<32>(tSp + 32, sv);
       tmem_ld_wait();
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_empty(g));
+      if (lane == 0) mbar_arrive(b_staken);
       if (nvalid < 64) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -822,13 +837,13 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       // P V_{j-1} of this half must be complete before O is touched or P overwritten
       bool waited = (j == 0);
       if (DEFER == 0 && !waited) {
-        mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+        mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
         fence_after_sync();
         waited = true;
       }
       if (__any_sync(0xffffffffu, grow)) {
         if (!waited) {
-          mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+          mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
           fence_after_sync();
           waited = true;
         }
@@ -883,7 +898,7 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
       for (int c = 0; c < DEFER; c += 8) early[c >> 3] = exp8(c);
       if (!waited) {
-        mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+        mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
         fence_after_sync();
       }
       if (SETREG) {
@@ -900,7 +915,7 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(g, h));
+      if (lane == 0) mbar_arrive(b_pfull);
     }
     // ---- merge the two halves of each row and write O / l as bf16 ----
     float2* xch = reinterpret_cast<float2*>(gen + xch_off);
@@ -975,29 +990,32 @@ constexpr size_t attn2h_smem_bytes() { return 1024 + (size_t)(2 + 3 + 3 + 4) * 1
 // Warps 0-15 softmax (quad = w&3, query tile g = (w>>2)&1, half h = w>>3), 16/17 MMA issue of tile 0/1, 18 TMA of Q and K,
 // 19 TMA of V + the ones column.
 // ------------------------------------------------------------------------------------------------------
-template <int KS, int DV, int PP16>
+template <int KS, int DV, int PP16, int KST, int VST>
 __global__ void __launch_bounds__(kAHThreads, 1)
 attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
               const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using namespace tc05;
   extern __shared__ uint8_t smem_raw[];
   constexpr uint32_t kChunk = 128 * 128;  // [128 rows][64 bf16] swizzled = 16 KB
-  constexpr int DCH = 2, KST = 2;
+  constexpr int DCH = 2;
   constexpr uint32_t kTmemCols = 512;
   static_assert(128 + 4 * DV <= 512 && DV % 16 == 0 && DV <= 128, "S (128 columns) and four accumulators must fit TMEM");
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sQ = base;                          // 2 tiles x DCH chunks
   const uint32_t sK = sQ + 2 * DCH * kChunk;         // KST x DCH chunks
-  const uint32_t sV = sK + KST * DCH * kChunk;       // DCH chunks
-  const uint32_t sP = sV + DCH * kChunk;             // chunk 2g+h = P of query tile g, key half h
+  const uint32_t sV = sK + KST * DCH * kChunk;       // VST x DCH chunks
+  const uint32_t sP = sV + VST * DCH * kChunk;       // chunk 2g+h = P of query tile g, key half h
   // (the running maxima of the h = 1 threads cross to their h = 0 partners through the head of tile g's own Q chunks,
   //  which nothing reads after that tile's last Q K^T)
   const uint32_t bars = sP + 4 * kChunk;
   const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u + 8u * s; };
   auto k_empty = [&](int s) { return bars + 24u + 8u * s; };
-  const uint32_t v_full = bars + 40u, v_empty = bars + 48u, v_ones = bars + 56u;
-  const uint32_t gbars = bars + 64u;
+  auto v_full = [&](int s) { return bars + 40u + 8u * s; };
+  auto v_empty = [&](int s) { return bars + 56u + 8u * s; };
+  auto v_ones = [&](int s) { return bars + 72u + 8u * s; };
+  const uint32_t gbars = bars + 88u;
+  static_assert(KST <= 2 && VST <= 2, "two barrier slots per ring");
   auto s_full = [&](int g) { return gbars + 8u * g; };
   auto s_taken = [&](int g) { return gbars + 16u + 8u * g; };
   auto p_full = [&](int g, int h) { return gbars + 32u + 8u * (2 * g + h); };
@@ -1015,7 +1033,7 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
     for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 2); }  // released by both tiles' MMA warps
-    mbar_init(v_full, 1); mbar_init(v_empty, 2); mbar_init(v_ones, 1);
+    for (int s = 0; s < VST; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 2); mbar_init(v_ones(s), 1); }
     for (int g = 0; g < 2; ++g) {
       mbar_init(s_full(g), 1);
       mbar_init(s_taken(g), 8);  // one arrive per softmax warp of the tile (both halves)
@@ -1085,7 +1103,8 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const uint32_t idesc_pv = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
       for (int j = 0; j < nkv; ++j) {
         if (j + 1 < nkv) issue_qk(j + 1);
-        mbar_wait(v_ones, (uint32_t)j & 1u);  // V tile landed and its ones column is in place
+        const int vs = j % VST;
+        mbar_wait(v_ones(vs), (uint32_t)(j / VST) & 1u);  // V tile landed and its ones column is in place
         fence_after_sync();
         const int ksteps = keys_in_tile(j) >> 4;
 #pragma unroll
@@ -1095,12 +1114,12 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const uint32_t tO = tmem + 128u + (uint32_t)(DV * (2 * g + h));
           const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * g + h) * kChunk, 16, 1024);
           for (int k = 4 * h; k < 4 * h + 4 && k < ksteps; ++k) {
-            const uint64_t db = make_smem_desc_sw128(sV + (uint32_t)k * 2048u, kChunk, 1024);
+            const uint64_t db = make_smem_desc_sw128(sV + (uint32_t)(vs * DCH) * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
             mma_f16_ss(tO, dp + 2 * (k & 3), db, idesc_pv, (j > 0) || (k > 4 * h));
           }
           mma_commit(o_done(g, h));
         }
-        mma_commit(v_empty);
+        mma_commit(v_empty(vs));
       }
     }
     __syncwarp();
@@ -1109,22 +1128,31 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // denominator (column d of O = sum_k P[q,k]) on the tensor core =====
     setmaxnreg_dec<kCtlRegs>();
     const uint32_t c64 = (uint32_t)p.d >> 6, chunk = ((uint32_t)(p.d & 63) * 2) >> 4, within = (uint32_t)(p.d * 2) & 15u;
-    for (int j = 0; j < nkv; ++j) {
-      if (lane == 0) {
-        if (j > 0) mbar_wait(v_empty, (uint32_t)(j - 1) & 1u);  // P V_{j-1} of both query tiles has completed
-        mbar_expect_tx(v_full, DCH * kChunk);
+    auto load_v = [&](int t) {  // lane 0: V tile t into its ring slot, once P V of the slot's previous tenant has completed
+      const int slot = t % VST;
+      mbar_wait(v_empty(slot), ((uint32_t)(t / VST) & 1u) ^ 1u);
+      mbar_expect_tx(v_full(slot), DCH * kChunk);
 #pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_4d(sV + c * kChunk, &tmV, v_full, 64 * c, head, j * 128, b);
-      }
+      for (int c = 0; c < DCH; ++c) tma_load_4d(sV + (slot * DCH + c) * kChunk, &tmV, v_full(slot), 64 * c, head, t * 128, b);
+    };
+    if (lane == 0)
+      for (int t = 0; t < VST - 1 && t < nkv; ++t) load_v(t);
+    for (int j = 0; j < nkv; ++j) {
+      if (VST == 1 && lane == 0) load_v(j);
       __syncwarp();
-      mbar_wait(v_full, (uint32_t)j & 1u);
-      uint8_t* vt = gen + (sV - base) + c64 * kChunk;
+      const int vs = j % VST;
+      mbar_wait(v_full(vs), (uint32_t)(j / VST) & 1u);
+      uint8_t* vt = gen + (sV - base) + (uint32_t)(vs * DCH + c64) * kChunk;
 #pragma unroll
       for (int r = lane; r < 128; r += 32)
         *reinterpret_cast<uint16_t*>(vt + r * 128 + ((chunk ^ (uint32_t)(r & 7)) << 4) + within) = 0x3F80;  // bf16 1.0
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(v_ones);
+      if (lane == 0) {
+        mbar_arrive(v_ones(vs));
+        if (VST > 1 && j + VST - 1 < nkv) load_v(j + VST - 1);  // prefetch after the patch: the patch never waits for a P V
+      }
+      __syncwarp();
     }
   } else if (warp < 16) {
     // ===== softmax: thread = (query row, key half) =====
@@ -1137,20 +1165,24 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int sw = row & 7;
     // 16-byte chunk c of this thread's P row sits at prow ^ (c << 4) (128-byte swizzle; bits 4-6 of the row start are 0)
     uint32_t prow = (sP + (uint32_t)(2 * g + h) * kChunk + (uint32_t)row * 128u) | ((uint32_t)sw << 4);
-    asm volatile("" : "+r"(prow));  // keep it in a register: ptxas otherwise recomputes it from %tid every tile
     float m_run = -INFINITY;  // (the running denominator lives in column d of the accumulator)
+    // loop-invariant addresses, pinned: ptxas otherwise rebuilds each of them from %tid and the shared window every tile
+    uint32_t b_sfull = s_full(g), b_staken = s_taken(g), b_pfull = p_full(g, h), b_odone = o_done(g, h), tSp = tS;
+    int last_valid = p.Nk - (nkv - 1) * 128 - 64 * h;  // valid keys of this half in the last tile (all others are full)
+    last_valid = last_valid < 0 ? 0 : (last_valid > 64 ? 64 : last_valid);
+    pin_reg(b_sfull, lane); pin_reg(b_staken, lane); pin_reg(b_pfull, lane); pin_reg(b_odone, lane); pin_reg(tSp, lane);
+    pin_reg(prow, lane);
     for (int j = 0; j < nkv; ++j) {
-      int nvalid = p.Nk - j * 128 - 64 * h;  // valid keys of this half
-      nvalid = nvalid < 0 ? 0 : (nvalid > 64 ? 64 : nvalid);
-      mbar_wait(s_full(g), (uint32_t)j & 1u);
+      const int nvalid = (j == nkv - 1) ? last_valid : 64;
+      mbar_wait(b_sfull, (uint32_t)j & 1u);
       fence_after_sync();
       uint32_t sv[64];
-      tmem_ld32_at<0>(tS, sv);
-      tmem_ld32_at<32>(tS + 32, sv);
+      tmem_ld32_at<0>(tSp, sv);
+      tmem_ld32_at<32>(tSp + 32, sv);
       tmem_ld_wait();
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(s_taken(g));
+      if (lane == 0) mbar_arrive(b_staken);
       if (nvalid < 64) {
 #pragma unroll
         for (int i = 0; i < 64; ++i)
@@ -1169,7 +1201,7 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       bool waited = (j == 0);  // P V_{j-1} of this half must be complete before O is touched or P overwritten
       if (__any_sync(0xffffffffu, grow)) {
         if (!waited) {
-          mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+          mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
           fence_after_sync();
           waited = true;
         }
@@ -1215,7 +1247,7 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       early[0] = exp8(0);
       early[1] = exp8(8);
       if (!waited) {
-        mbar_wait(o_done(g, h), (uint32_t)(j - 1) & 1u);
+        mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
         fence_after_sync();
       }
       st_shared_v4(prow, early[0]);
@@ -1225,7 +1257,7 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       fence_proxy_async_smem();  // P (generic proxy) -> visible to the tensor core's async proxy
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full(g, h));
+      if (lane == 0) mbar_arrive(b_pfull);
     }
     // ---- merge the two halves of each row and write O / l as bf16 ----
     float* xch = reinterpret_cast<float*>(gen + (sQ - base) + (uint32_t)(g * DCH) * kChunk);
@@ -1288,7 +1320,8 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   if (warp == 16) tmem_dealloc(tmem, kTmemCols);
 }
 
-constexpr size_t attn2x_smem_bytes() { return 1024 + (size_t)(4 + 4 + 2 + 4) * 128 * 128 + 64 + 96 + 16 + 16; }
+template <int KST, int VST>
+constexpr size_t attn2x_smem_bytes() { return 1024 + (size_t)(4 + 2 * KST + 2 * VST + 4) * 128 * 128 + 88 + 96 + 16 + 16; }
 
 
 
@@ -1834,7 +1867,8 @@ inline void init_attn_kernels() {
                                  (int)attn2q_smem_bytes<2, 2, 1>()));
   SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
   SDTF_CUDA(cudaFuncSetAttribute(attn2h_kernel<3, 48, 16, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2h_smem_bytes()));
-  SDTF_CUDA(cudaFuncSetAttribute(attn2x_kernel<5, 96, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2x_smem_bytes()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2x_kernel<5, 96, 3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2x_smem_bytes<2, 1>()));
+  SDTF_CUDA(cudaFuncSetAttribute(attn2x_kernel<5, 96, 3, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn2x_smem_bytes<1, 2>()));
   init_attn_t<2, 5, 80, 2, 2>();
   init_attn_t<3, 10, 160, 1, 1>();
   SDTF_CUDA(cudaFuncSetAttribute(vattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vattn_smem_bytes()));
@@ -1898,10 +1932,10 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
       static const int use_2q = getenv("SDTF_ATTN_2Q") ? atoi(getenv("SDTF_ATTN_2Q")) : 0;  // A/B: previous full-row kernel
       if (!use_2q) {
         SDTF_CHECK(a.d < 48, "attn2h keeps the softmax denominator in accumulator column d: needs d < DV");
-        // SDTF_ATTN_SETREG=0 (A/B): the kernel without the per-role register budget and the direct P stores.
+        // SDTF_ATTN_SETREG=0 (A/B): the kernel without the per-role register budgets, pinned addresses and direct P stores.
         // Tuning history of the two other knobs: 3 of every 8 exponential pairs on the FMA pipe (0.725 / 0.749 / 0.702 /
-        // 0.754 ms for scalar code, 2, 3, 4 of 8) and the first 16 keys' exponentials before the wait for P V_{j-1}
-        // (0.674 / 0.665 / 0.693 ms for 0 / 16 / 32), profiles/r02_b_attn2h_packed_exp.log, r02_u_attn_ab.log.
+        // 0.754 ms for scalar code, 2, 3, 4 of 8; 0.679 / 0.617 / 0.639 / 0.703 for 2, 3, 4, 5 in the final kernel) and the first 16 keys' exponentials before the wait for P V_{j-1}
+        // (0.625 / 0.617 / 0.645 / 0.682 ms for 8 / 16 / 24 / 32), profiles/r02_b_attn2h_packed_exp.log, r02_u_*.log.
         static const int setreg = getenv("SDTF_ATTN_SETREG") ? atoi(getenv("SDTF_ATTN_SETREG")) : 1;
         const size_t sm = attn2h_smem_bytes();
         if (setreg) launch_pdl(attn2h_kernel<3, 48, 16, 3, true>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
@@ -1929,7 +1963,8 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
     } else {  // two query tiles per CTA, warp-specialised (softmax of one tile overlaps the MMAs of the other)
       dim3 grid((unsigned)ceil_div(a.Nq, 256), (unsigned)a.heads, (unsigned)a.B);
       static const int use_2x = getenv("SDTF_ATTN_2X") ? atoi(getenv("SDTF_ATTN_2X")) : 1;  // A/B: 0 = full-row kernel (round 1)
-      if (use_2x) launch_pdl(attn2x_kernel<5, 96, 3>, grid, dim3(kAHThreads), attn2x_smem_bytes(), stream, 1, tq, tk, tv, p);
+      if (use_2x == 2) launch_pdl(attn2x_kernel<5, 96, 3, 2, 1>, grid, dim3(kAHThreads), attn2x_smem_bytes<2, 1>(), stream, 1, tq, tk, tv, p);
+      else if (use_2x) launch_pdl(attn2x_kernel<5, 96, 3, 1, 2>, grid, dim3(kAHThreads), attn2x_smem_bytes<1, 2>(), stream, 1, tq, tk, tv, p);
       else launch_pdl(attn2q_kernel<2, 5, 80, 2, 1>, grid, dim3(kA2Threads), attn2q_smem_bytes<2, 2, 1>(), stream, 1, tq, tk, tv, p);
     }
   } else if (a.d == 160) {
