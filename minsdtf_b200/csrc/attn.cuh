@@ -270,26 +270,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
-// Packed fp32 pairs (sm_100 FFMA2 / FADD2: one issue slot for two lanes' worth of FMA work).  The softmax warps of the
-// d = 40 kernel are bound by instruction issue and by the 16-lane MUFU together (ncu r01: issue 64 %, xu 52 %), so the
-// scale-and-subtract of every score and the polynomial 2^x run as pairs.
-using f32x2 = unsigned long long;
-__device__ __forceinline__ f32x2 pack2(float a, float b) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
+using tc05::f32x2; using tc05::pack2; using tc05::unpack2; using tc05::fma2; using tc05::add2;  // packed fp32 pairs (tc05.cuh)
 // 2^x for a pair on the FMA / ALU pipes (same Cody-Waite split + cubic as ex2_poly); inputs are clamped to >= -126
 __device__ __forceinline__ void ex2_poly2(f32x2 x2, float& e0, float& e1) {
   float x0, x1;

@@ -14,8 +14,8 @@
 //     FLOP further; above 256 columns the accumulator is single-buffered (512 TMEM columns), which long-K convs
 //     amortise.  Measured (ncu, 3x3 conv): tensor pipe 50 % busy at 256x160 tiles, 80 % at 256x256 — the L2 -> SM
 //     path delivers ~50 B/clk/SM, so tile area per byte is what sets the rate.
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (pair: leader CTA only) and TMEM owner, warps 2-5 = epilogue,
-// warp 6 = store warp (TMA stores of staged sub-tiles, residual prefetch / buffer grants).
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (pair: leader CTA only) and TMEM owner, warps 2-3 = store warps (TMA
+// stores of staged sub-tiles, residual prefetch / buffer grants; one per epilogue set), warps 4-11 = epilogue (two sets).
 // Pipelines: smem ring full/empty (TMA <-> MMA), TMEM accumulators tfull/tempty (MMA <-> epilogue), four staging
 // buffers: grant (res_bar: buffer free, residual landed) -> epilogue -> stg_full -> store warp -> bulk-group wait.
 #pragma once
@@ -135,7 +135,8 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int m_units = (x.m_tiles + CG - 1) / CG;
   const int total_units = m_units * x.n_tiles * x.splits;
   constexpr bool kAll = MODE == G3_GENERAL;
-  constexpr bool kGeglu = kAll || MODE == G3_GEGLU || MODE == G3_GEGLU_LN, kLnOut = kAll || MODE == G3_LN_PRODUCE,
+  constexpr bool kGegluOnly = MODE == G3_GEGLU || MODE == G3_GEGLU_LN;
+  constexpr bool kLnOut = kAll || MODE == G3_LN_PRODUCE,
                  kLnIn = kAll || MODE == G3_LN_APPLY || MODE == G3_GEGLU_LN;
   const bool partial_mode = kAll && x.partial != nullptr;
   const int unit0 = (int)blockIdx.x / CG, unit_step = (int)gridDim.x / CG;
@@ -301,20 +302,24 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (prof_on) { prof[2] = w_full; prof[3] = w_tempty; prof[4] = clock64() - t_start; }
     }
     __syncwarp();
-  } else if (warp == 2) {
-    // ===== store warp: TMA stores of staged sub-tiles; grants staging buffers (with the residual tile when there is one)
+  } else if (warp == 2 || warp == 3) {
+    // ===== store warps: TMA stores of staged sub-tiles; grant staging buffers (with the residual tile when there is one).
+    // One elected thread each: warp 2 serves the passes of even global index (epilogue set 0 and the even buffers), warp 3
+    // the odd ones.  A single store thread was what bounded the short-K linears: ~700 cycles of serial bookkeeping per
+    // pass (wait, coordinates, store, commit, read-wait, grant) against one pass per ~720 cycles measured at 320 -> 1536
+    // (per-role counters: that thread busy 84 %, the MMA warp waiting for accumulators 41 % of the time).
     // (split-K partial sums leave straight from the epilogue warps' registers: nothing to stage)
     if (!partial_mode && elect_one()) {
-      const bool geglu = kGeglu && (p.act == ACT_GEGLU);
+      const int par = warp - 2;
       const int ncols = x.ncols;
       const int passes = (ncols + 31) >> 5;
       const bool has_res = p.res != nullptr;
       auto pass_col = [&](int ps) { return (ps * 32 + 32 <= ncols || ncols < 32) ? ps * 32 : ncols - 32; };
-      (void)geglu;
       const int my_units = unit0 < total_units ? (total_units - unit0 + unit_step - 1) / unit_step : 0;
       const int total_passes = my_units * passes;
-      // grant cursor: pass gg = (unit gu, pass gps) may use buffer gg & nb_mask
-      int gu = unit0, gps = 0, gg = 0;
+      // grant cursor: pass gg = (unit gu, pass gps) of this thread's parity may use buffer gg & nb_mask
+      int gu = unit0, gps = par, gg = par;
+      while (gps >= passes) { gps -= passes; gu += unit_step; }
       auto grant = [&]() {
         if (gg >= total_passes) return;
         const int buf = gg & nb_mask;
@@ -327,33 +332,35 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         } else {
           mbar_arrive(res_bar(buf));
         }
-        ++gg;
-        if (++gps == passes) { gps = 0; gu += unit_step; }
+        gg += 2; gps += 2;
+        while (gps >= passes) { gps -= passes; gu += unit_step; }
       };
-      for (int k = 0; k < kG3Bufs; ++k) grant();
+      for (int k = par; k < kG3Bufs; k += 2) grant();
       long long w_stg = 0, w_read = 0;
-      int sg = 0;
-      for (int u = unit0; u < total_units; u += unit_step) {
-        int n_tile, x0, y0, b0;
-        tile_coords(u, n_tile, x0, y0, b0);
-        for (int ps = 0; ps < passes; ++ps, ++sg) {
-          const int buf = sg & nb_mask;
-          // all 4 epilogue warps staged (and fenced) their rows
-          G3_TIMED(prof_on, w_stg, mbar_wait(stg_bar(buf), (uint32_t)(sg >> nb_shift) & 1u));
-          const int col = n_tile * ncols + pass_col(ps);
-          const uint32_t src = smem_base + stg_off + (uint32_t)buf * kG3BufBytes;
-          if (x.head_stride) tma_store_5d(&tmOut, src, col % x.head_stride, col / x.head_stride, x0, y0, b0);
-          else tma_store_4d(&tmOut, src, col, x0, y0, b0);
-          bulk_commit();
-          if (sg >= 1) {
-            // store sg-1 no longer reads its buffer: it can host pass sg-1+kG3Bufs
-            G3_TIMED(prof_on, w_read, bulk_wait_read<1>());
-            grant();
-          }
+      int su = unit0, sps = par, issued = 0;
+      while (sps >= passes) { sps -= passes; su += unit_step; }
+      int n_tile = 0, x0 = 0, y0 = 0, b0 = 0, cu = -1;
+      for (int sg = par; sg < total_passes; sg += 2) {
+        if (su != cu) { tile_coords(su, n_tile, x0, y0, b0); cu = su; }
+        const int buf = sg & nb_mask;
+        // all 4 epilogue warps of the set staged (and fenced) their rows
+        G3_TIMED(prof_on, w_stg, mbar_wait(stg_bar(buf), (uint32_t)(sg >> nb_shift) & 1u));
+        const int col = n_tile * ncols + pass_col(sps);
+        const uint32_t src = smem_base + stg_off + (uint32_t)buf * kG3BufBytes;
+        if (x.head_stride) tma_store_5d(&tmOut, src, col % x.head_stride, col / x.head_stride, x0, y0, b0);
+        else tma_store_4d(&tmOut, src, col, x0, y0, b0);
+        bulk_commit();
+        if (issued >= 1) {
+          // this thread's previous store no longer reads its buffer: it can host that pass + kG3Bufs
+          G3_TIMED(prof_on, w_read, bulk_wait_read<1>());
+          grant();
         }
+        ++issued;
+        sps += 2;
+        while (sps >= passes) { sps -= passes; su += unit_step; }
       }
       bulk_wait_all();
-      if (prof_on) { prof[5] = w_stg; prof[6] = w_read; prof[7] = clock64() - t_start; }
+      if (prof_on && par == 0) { prof[5] = w_stg; prof[6] = w_read; prof[7] = clock64() - t_start; }
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -363,7 +370,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int set = (warp - 4) >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
-    const bool geglu = kGeglu && (p.act == ACT_GEGLU);
+    const bool geglu = kGegluOnly || (kAll && p.act == ACT_GEGLU);  // (the GEGLU instantiations carry no other path)
     const int ncols = x.ncols;
     const int Nout = geglu ? p.N / 2 : p.N;
     float2* const ln_out = kLnOut ? p.ln_out : nullptr;
@@ -372,7 +379,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int sw = (row >> 1) & 3;  // 64-byte swizzle: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
     auto pass_col = [&](int ps) { return (ps * 32 + 32 <= ncols || ncols < 32) ? ps * 32 : ncols - 32; };
 
-    long long w_tfull = 0, w_grant = 0;
+    long long w_tfull = 0, w_grant = 0, w_ld = 0, w_stage = 0, w_vec = 0;
     const int et = (int)threadIdx.x - 128;  // 0..255 (set 0: 0..127)
     const bool ln_apply = kLnIn && p.ln_in != nullptr;
     const bool has_vec = p.bias != nullptr || p.temb != nullptr || ln_apply;
@@ -437,6 +444,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       G3_TIMED(prof_on, w_tfull, mbar_wait(tfull_bar(acc), (uint32_t)(x.acc_bufs == 2 ? lt >> 1 : lt) & 1u));
       fence_after_sync();
       float* vtile = vec + (size_t)(lt & 1) * vrows * vwidth;
+      const long long t_v0 = prof_on ? clock64() : 0;
       if (has_vec) {
         if (vcol < vwidth) {
 #pragma unroll
@@ -445,6 +453,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
         epi_set_bar_sync(set);  // vector visible to the set's four warps; also: they are done reading the tile before last's copy
       }
+      if (prof_on) w_vec += clock64() - t_v0;
       const float* vrow = vtile + vr * vwidth;
       if (ps0 >= passes) {  // no pass of this tile is ours: nothing to read from the accumulator
         fence_before_sync();
@@ -492,7 +501,9 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int tc = pass_col(ps);          // column inside the tile's output slice
         uint32_t v[32];
         float f[32];
+        const long long t_ld0 = prof_on ? clock64() : 0;
         tmem_ld32(t_row + (uint32_t)tc, v);
+        if (prof_on && !geglu) { tmem_ld_wait(); w_ld += clock64() - t_ld0; }
         if (geglu) {
           uint32_t gv[32];
           tmem_ld32(t_row + (uint32_t)(ncols + tc), gv);
@@ -510,10 +521,24 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               bv.x = fmaf(ln_b, cv.x, bv.x); bv.y = fmaf(ln_b, cv.y, bv.y); bv.z = fmaf(ln_b, cv.z, bv.z); bv.w = fmaf(ln_b, cv.w, bv.w);
               bg.x = fmaf(ln_b, cg.x, bg.x); bg.y = fmaf(ln_b, cg.y, bg.y); bg.z = fmaf(ln_b, cg.z, bg.z); bg.w = fmaf(ln_b, cg.w, bg.w);
             }
-            f[i] = fmaf(ln_a, __uint_as_float(v[i]), bv.x) * gelu_tanh_fast(fmaf(ln_a, __uint_as_float(gv[i]), bg.x));
-            f[i + 1] = fmaf(ln_a, __uint_as_float(v[i + 1]), bv.y) * gelu_tanh_fast(fmaf(ln_a, __uint_as_float(gv[i + 1]), bg.y));
-            f[i + 2] = fmaf(ln_a, __uint_as_float(v[i + 2]), bv.z) * gelu_tanh_fast(fmaf(ln_a, __uint_as_float(gv[i + 2]), bg.z));
-            f[i + 3] = fmaf(ln_a, __uint_as_float(v[i + 3]), bv.w) * gelu_tanh_fast(fmaf(ln_a, __uint_as_float(gv[i + 3]), bg.w));
+            // value * gelu(gate) on packed pairs: 8 FMA-pipe instructions + 2 MUFU.TANH per two outputs (scalar: 22 + 2)
+            const f32x2 la2 = pack2(ln_a, ln_a);
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              const int k = i + 2 * h2;
+              const f32x2 bv2 = h2 ? pack2(bv.z, bv.w) : pack2(bv.x, bv.y), bg2 = h2 ? pack2(bg.z, bg.w) : pack2(bg.x, bg.y);
+              f32x2 val = pack2(__uint_as_float(v[k]), __uint_as_float(v[k + 1]));
+              f32x2 gate = pack2(__uint_as_float(gv[k]), __uint_as_float(gv[k + 1]));
+              if (ln_apply) { val = fma2(la2, val, bv2); gate = fma2(la2, gate, bg2); }
+              else { val = add2(val, bv2); gate = add2(gate, bg2); }
+              // gelu(g) = 0.5 g (1 + tanh(g (0.79788456 + 0.03567741 g^2)))
+              const f32x2 inner = fma2(mul2(gate, gate), pack2(0.0356774081f, 0.0356774081f), pack2(0.7978845608f, 0.7978845608f));
+              float u0, u1;
+              unpack2(mul2(inner, gate), u0, u1);
+              const f32x2 th = pack2(tanh_approx(u0), tanh_approx(u1));
+              const f32x2 hv = mul2(mul2(gate, pack2(0.5f, 0.5f)), val);  // 0.5 g v
+              unpack2(fma2(hv, th, hv), f[k], f[k + 1]);
+            }
           }
         } else {
           tmem_ld_wait();
@@ -571,6 +596,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           for (int i = 0; i < 32; ++i) f[i] = qgelu_f(f[i]);
         }
         float ln_s1 = 0.f, ln_s2 = 0.f;
+        const long long t_st0 = prof_on ? clock64() : 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 o;
@@ -595,12 +621,15 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         // number of M tiles, i.e. the batch: a sample's statistics must not depend on what it is batched with.
         if (ln_out && ln_m >= 0)
           ln_out[(long long)((n_tile * ncols + tc) >> 5) * p.ln_rows + ln_m] = make_float2(ln_s1, ln_s2);
+        // (deferring this hand-over by one pass, so that the fence finds the stores long complete, was slower: with two
+        //  staging buffers per set the later store delays the grant the set needs two passes on — 63.5 -> 68 us at 320 -> 1536)
         fence_proxy_async_smem();  // staged row (generic proxy) -> visible to the TMA store (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(stg_bar(buf));
+        if (prof_on) w_stage += clock64() - t_st0;
       }
     }
-    if (prof_on && threadIdx.x == 128) { prof[8] = w_tfull; prof[9] = w_grant; prof[10] = clock64() - t_start; prof[11] = lt; }
+    if (prof_on && threadIdx.x == 128) { prof[8] = w_tfull; prof[9] = w_grant; prof[10] = clock64() - t_start; prof[11] = lt; prof[12] = w_ld; prof[13] = w_stage; prof[14] = w_vec; }
   }
 
   // teardown: everyone (in both CTAs of a pair) done with TMEM before the allocating warp frees it

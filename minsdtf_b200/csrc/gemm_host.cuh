@@ -386,6 +386,7 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
       const int cg = plan.cg;
       const size_t stage_bytes = kATileBytes + (size_t)(p.BN / cg) * 128;
       x.nbufs = (a.res && !split) ? kG3MaxBufs : 4;  // residual tiles are TMA-prefetched nbufs-1 passes ahead: latency needs depth
+      // (eight buffers without a residual, where they cost no ring stage: no change — 64.0 against 64.1 us at 320 -> 1536)
       const int kG3Bufs = x.nbufs;
       const size_t fixed = 1024 + (size_t)kG3Bufs * kG3BufBytes + 8 * (2 * 10 + 4 + 2 * kG3Bufs) + 32 + vec_bytes;
       int st = (int)((kSmemLimit - fixed) / stage_bytes);
@@ -474,9 +475,9 @@ inline void launch_conv(cudaStream_t stream, const ConvArgs& a) {
           for (int k = 0; k < 16; ++k) a[k] += (double)h[b * 16 + k] / grid;
         fprintf(stderr,
                 "[gemm3-prof] N %d iters %d CG %d BN %d | producer wait_empty %.0f / %.0f | mma wait_full %.0f wait_tempty %.0f / %.0f | "
-                "store wait_stg %.0f wait_read %.0f / %.0f | epi wait_tfull %.0f wait_grant %.0f / %.0f tiles %.1f (cycles, avg per CTA; "
-                "mma counters are per leader CTA x1/CG)\n",
-                w.N, iters, cg, p.BN, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]);
+                "store wait_stg %.0f wait_read %.0f / %.0f | epi wait_tfull %.0f wait_grant %.0f tmem_ld %.0f pack+stage+fence %.0f vec+bar %.0f / %.0f tiles "
+                "%.1f (cycles, avg per CTA; mma counters are per leader CTA x1/CG)\n",
+                w.N, iters, cg, p.BN, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[12], a[13], a[14], a[10], a[11]);
       }
       static const int verbose = env_int("SDTF_GEMM_VERBOSE", 0);
       if (verbose)

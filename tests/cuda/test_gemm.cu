@@ -384,6 +384,10 @@ int main(int argc, char** argv) {
       {"linear_n1280_bn80_res",    1, 1, 1024, 1280,  0, 1280, 1, 1, 1, 0, 0, 1, 1024, true, false, true, false, ACT_NONE, 80, 0},
       {"linear_geglu_m1000",       1, 1, 1000, 640,   0, 5120, 1, 1, 1, 0, 0, 1, 1000, true, false, false, false, ACT_GEGLU, 0, 0},
       {"conv3x3_96ch_slice_res",   2, 32, 32,  96,  0,  96, 3, 3, 1, 1, 1, 32, 32, true, false, true, false, ACT_NONE, 0, 32},
+      // K = 320 linears with many M units per N tile (a one-tile-deep ring: stages == k-iterations)
+      {"linear_k320_n960_res",     1, 1, 16384, 320,  0, 960, 1, 1, 1, 0, 0, 1, 16384, true, false, true, false, ACT_NONE, 0, 0},
+      {"linear_k320_m16000_n320",  1, 1, 16000, 320,  0, 320, 1, 1, 1, 0, 0, 1, 16000, true, false, false, false, ACT_SILU, 0, 0},
+      {"linear_k320_geglu",        1, 1, 16384, 320,  0, 2560, 1, 1, 1, 0, 0, 1, 16384, true, false, false, false, ACT_GEGLU, 0, 0},
       // split-K (few tiles, long K): CTA pairs with BN 320, one-CTA units, concat K loop, residual, SiLU, strided view, stride 2
       {"splitk_8x8_b16_1280_temb", 16, 8, 8, 1280,  0, 1280, 3, 3, 1, 1, 1, 8, 8, true, true, false, false, ACT_NONE, 0, 0},
       {"splitk_8x8_b16_cat_res",   16, 8, 8, 1280, 1280, 1280, 3, 3, 1, 1, 1, 8, 8, true, false, true, false, ACT_NONE, 0, 0},
