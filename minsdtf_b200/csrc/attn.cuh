@@ -27,6 +27,7 @@ struct AttnParams {
   long long ldo;
   long long* prof;   // optional [16] global cycle counters summed over CTAs (SDTF_ATTN_PROFILE=1), null: off
   int debug;         // timing experiments only (SDTF_ATTN_DEBUG; results are garbage): 1 no exp, 2 no max, 4 no S load, 8 no P store, 16 no PV MMAs, 32 no QK MMAs, 64 no K/V TMA
+  int heads, n_qt, n_items;  // persistent kernels (attn2h): work items = (batch, head, 256-query tile), item = (b * heads + head) * n_qt + qt
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -633,8 +634,8 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const uint32_t sK = sQ + 2 * kChunk;            // KST chunks
   const uint32_t sV = sK + KST * kChunk;          // VST chunks
   const uint32_t sP = sV + VST * kChunk;          // chunk 2g+h = P of query tile g, key half h
-  const uint32_t xch_off = (sP - base) + 4 * kChunk;  // float2 [256]: (m, l) of the h = 1 threads for the final merge
-  const uint32_t bars = base + xch_off + 2048u;
+  const uint32_t xch_off = (sP - base) + 4 * kChunk;  // float2 [2][256]: (m, l) of the h = 1 threads for the final merge (by item parity)
+  const uint32_t bars = base + xch_off + 4096u;
   const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u + 8u * s; };
   auto k_empty = [&](int s) { return bars + 8u + 8u * (KST + s); };
@@ -646,18 +647,29 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   auto p_full = [&](int g, int h) { return gbars + 32u + 8u * (2 * g + h); };
   auto o_done = [&](int g, int h) { return gbars + 64u + 8u * (2 * g + h); };
   auto v_ones = [&](int s) { return gbars + 96u + 8u * s; };
-  const uint32_t tmem_slot = gbars + 96u + 8u * VST;
+  const uint32_t q_empty = gbars + 96u + 8u * VST;   // every Q K^T of the item has completed: Q may be overwritten
+  auto o_free = [&](int g) { return gbars + 104u + 8u * VST + 8u * g; };  // the merge has read tile g's accumulators
+  const uint32_t tmem_slot = gbars + 120u + 8u * VST;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
   const int nkv = (p.Nk + 127) / 128;
+  // Persistent: CTA c works on items c, c + gridDim.x, ... (consecutive items share a head's K / V).  Barrier phases run on
+  // the CTA-wide key-tile counter t, Q / accumulator hand-overs on the item counter, so the TMA and MMA warps run into the
+  // next item while the softmax warps merge and store the current one: the ~5 us of launch, TMEM allocation, first loads
+  // and epilogue that each 44-us CTA of the one-item-per-CTA grid paid are hidden (SDTF_ATTN_PERSIST=0: one item per CTA).
+  auto item_coords = [&](int item, int& q0, int& head, int& b) {
+    const int qt = item % p.n_qt, hb = item / p.n_qt;
+    q0 = qt * 256; head = hb % p.heads; b = hb / p.heads;
+  };
 
   pdl_trigger();
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 2);  // both tiles' MMA warps
+    for (int g = 0; g < 2; ++g) mbar_init(o_free(g), 4);  // the four h = 0 warps of the tile
     for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 2); }  // released by both tiles' MMA warps
     for (int s = 0; s < VST; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 2); mbar_init(v_ones(s), 1); }
     for (int g = 0; g < 2; ++g) {
@@ -690,17 +702,23 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // ===== TMA producer =====
     if (SETREG) setmaxnreg_dec<kCtlRegs>();
     if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * kChunk);
-      tma_load_4d(sQ, &tmQ, q_full, 0, head, q0, b);
-      tma_load_4d(sQ + kChunk, &tmQ, q_full, 0, head, q0 + 128, b);
-      for (int j = 0; j < nkv; ++j) {
-        const int ks = j % KST, vs = j % VST;
-        mbar_wait(k_empty(ks), ((uint32_t)(j / KST) & 1u) ^ 1u);
-        mbar_expect_tx(k_full(ks), kChunk);
-        tma_load_4d(sK + ks * kChunk, &tmK, k_full(ks), 0, head, j * 128, b);
-        mbar_wait(v_empty(vs), ((uint32_t)(j / VST) & 1u) ^ 1u);
-        mbar_expect_tx(v_full(vs), kChunk);
-        tma_load_4d(sV + vs * kChunk, &tmV, v_full(vs), 0, head, j * 128, b);
+      int t = 0, it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        int q0, head, b;
+        item_coords(item, q0, head, b);
+        if (it > 0) mbar_wait(q_empty, (uint32_t)(it - 1) & 1u);
+        mbar_expect_tx(q_full, 2 * kChunk);
+        tma_load_4d(sQ, &tmQ, q_full, 0, head, q0, b);
+        tma_load_4d(sQ + kChunk, &tmQ, q_full, 0, head, q0 + 128, b);
+        for (int j = 0; j < nkv; ++j, ++t) {
+          const int ks = t % KST, vs = t % VST;
+          mbar_wait(k_empty(ks), ((uint32_t)(t / KST) & 1u) ^ 1u);
+          mbar_expect_tx(k_full(ks), kChunk);
+          tma_load_4d(sK + ks * kChunk, &tmK, k_full(ks), 0, head, j * 128, b);
+          mbar_wait(v_empty(vs), ((uint32_t)(t / VST) & 1u) ^ 1u);
+          mbar_expect_tx(v_full(vs), kChunk);
+          tma_load_4d(sV + vs * kChunk, &tmV, v_full(vs), 0, head, j * 128, b);
+        }
       }
     }
     __syncwarp();
@@ -711,44 +729,54 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const int g = warp - 16;
       const uint32_t tS = tmem + 128u * g;
       const uint64_t dq = make_smem_desc_sw128(sQ + g * kChunk, 16, 1024);
-      auto issue_qk = [&](int j) {
-        const int st = j % KST;
-        const uint32_t idesc = make_idesc_bf16(128, keys_in_tile(j), 0, 0);
+      // (this thread lives on 32 registers: ring slot / phase / tile parity are carried incrementally instead of being
+      //  derived from a tile counter, and the two instruction descriptors of Q K^T are built once)
+      static_assert(KST == VST, "the K and V rings advance together");
+      const uint32_t idesc_pv = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
+      int ks = 0;                  // ring slot of the current tile
+      uint32_t kph = 0, tpar = 0;  // its ring phase; parity of the CTA-wide tile counter
+      bool any = false;            // a tile has been issued before (the S buffer / P chunks have a previous tenant)
+      // Q K^T of the tile in ring slot `st` / phase `ph`: waits for K and for the softmax warps to have pulled the previous S
+      auto issue_qk = [&](int st, uint32_t ph, uint32_t prev_par, bool last) {
+        mbar_wait_lean(k_full(st), ph);
+        if (any) mbar_wait_lean(s_empty(g), prev_par);
+        fence_after_sync();
         const uint64_t dk = make_smem_desc_sw128(sK + st * kChunk, 16, 1024);
+        const uint32_t idesc = make_idesc_bf16(128, last ? keys_in_tile(nkv - 1) : 128, 0, 0);
 #pragma unroll
         for (int k = 0; k < KS; ++k) mma_f16_ss(tS, dq + 2 * k, dk + 2 * k, idesc, k != 0);
         mma_commit(s_full(g));
         mma_commit(k_empty(st));
+        any = true;
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full(0), 0);
-      fence_after_sync();
-      issue_qk(0);
-      const uint32_t idesc_pv = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) {
-          mbar_wait(k_full((j + 1) % KST), (uint32_t)((j + 1) / KST) & 1u);
-          mbar_wait(s_empty(g), (uint32_t)j & 1u);  // both halves of S_j are in registers
+      const int my_items = (int)blockIdx.x < p.n_items ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+      for (int it = 0; it < my_items; ++it) {
+        mbar_wait_lean(q_full, (uint32_t)it & 1u);
+        issue_qk(ks, kph, tpar ^ 1u, nkv == 1);
+        for (int j = 0; j < nkv; ++j) {
+          const int ks1 = ks + 1 == KST ? 0 : ks + 1;
+          const uint32_t kph1 = ks + 1 == KST ? kph ^ 1u : kph;
+          if (j + 1 < nkv) issue_qk(ks1, kph1, tpar, j + 2 == nkv);
+          else mma_commit(q_empty);  // arrives when every Q K^T of this item has completed
+          mbar_wait_lean(v_ones(ks), kph);  // V tile landed and its ones column is in place
+          if (j == 0 && it > 0) mbar_wait_lean(o_free(g), (uint32_t)(it - 1) & 1u);  // the previous item's merge has read O
           fence_after_sync();
-          issue_qk(j + 1);
-        }
-        const int vs = j % VST;
-        mbar_wait(v_ones(vs), (uint32_t)(j / VST) & 1u);  // V tile landed and its ones column is in place
-        fence_after_sync();
-        const int ksteps = keys_in_tile(j) >> 4;
+          const int ksteps = j + 1 == nkv ? (keys_in_tile(nkv - 1) >> 4) : 8;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(p_full(g, h), (uint32_t)j & 1u);  // this half of P_j is in shared memory
-          fence_after_sync();
-          const uint32_t tO = tmem + 256u + (uint32_t)(DV * (2 * g + h));
-          const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * g + h) * kChunk, 16, 1024);
-          for (int k = 4 * h; k < 4 * h + 4 && k < ksteps; ++k) {
-            const uint64_t db = make_smem_desc_sw128(sV + vs * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
-            mma_f16_ss(tO, dp + 2 * (k & 3), db, idesc_pv, (j > 0) || (k > 4 * h));
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait_lean(p_full(g, h), tpar);  // this half of P_j is in shared memory
+            fence_after_sync();
+            const uint32_t tO = tmem + 256u + (uint32_t)(DV * (2 * g + h));
+            const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * g + h) * kChunk, 16, 1024);
+            for (int k = 4 * h; k < 4 * h + 4 && k < ksteps; ++k) {
+              const uint64_t db = make_smem_desc_sw128(sV + ks * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
+              mma_f16_ss(tO, dp + 2 * (k & 3), db, idesc_pv, (j > 0) || (k > 4 * h));
+            }
+            mma_commit(o_done(g, h));
           }
-          mma_commit(o_done(g, h));
+          mma_commit(v_empty(ks));
+          ks = ks1; kph = kph1; tpar ^= 1u;
         }
-        mma_commit(v_empty(vs));
       }
     }
     __syncwarp();
@@ -757,7 +785,8 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // (column d of O = sum_k P[q,k]) on the tensor core instead of one FADD per exponential in the softmax warps
     if (SETREG) setmaxnreg_dec<kCtlRegs>();
     const uint32_t chunk = (uint32_t)(p.d * 2) >> 4, within = (uint32_t)(p.d * 2) & 15u;
-    for (int j = 0; j < nkv; ++j) {
+    const int my_items = (int)blockIdx.x < p.n_items ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    for (int j = 0; j < my_items * nkv; ++j) {
       const int vs = j % VST;
       mbar_wait(v_full(vs), (uint32_t)(j / VST) & 1u);
       uint8_t* vt = gen + (sV - base) + (uint32_t)vs * kChunk;
@@ -780,18 +809,23 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int sw = row & 7;
     // 16-byte chunk c of this thread's P row sits at prow ^ (c << 4) (128-byte swizzle; bits 4-6 of the row start are 0)
     uint32_t prow = (sP + (uint32_t)(2 * g + h) * kChunk + (uint32_t)row * 128u) | ((uint32_t)sw << 4);
-    float m_run = -INFINITY;  // (the running denominator lives in column d of the accumulator)
-    // loop-invariant addresses, pinned: ptxas otherwise rebuilds each of them from %tid and the shared window every tile
-    uint32_t b_sfull = s_full(g), b_staken = s_empty(g), b_pfull = p_full(g, h), b_odone = o_done(g, h), tSp = tS;
+    // loop-invariant addresses, pinned: ptxas otherwise rebuilds each of them from %tid and the shared window every tile.
+    // s_empty(g) = s_full(g) + 16 and o_done(g, h) = p_full(g, h) + 32 by the barrier layout above.
+    uint32_t b_sfull = s_full(g), b_pfull = p_full(g, h), tSp = tS;
     int last_valid = p.Nk - (nkv - 1) * 128 - 64 * h;  // valid keys of this half in the last tile (all others are full)
     last_valid = last_valid < 0 ? 0 : (last_valid > 64 ? 64 : last_valid);
     if (SETREG) {
-      pin_reg(b_sfull, lane); pin_reg(b_staken, lane); pin_reg(b_pfull, lane); pin_reg(b_odone, lane); pin_reg(tSp, lane);
+      pin_reg(b_sfull, lane); pin_reg(b_pfull, lane); pin_reg(tSp, lane);
       pin_reg(prow, lane);
     }
-    for (int j = 0; j < nkv; ++j) {
-      const int nvalid = (j == nkv - 1) ? last_valid : 64;
-      mbar_wait(b_sfull, (uint32_t)j & 1u);
+    const uint32_t b_staken = b_sfull + 16u, b_odone = b_pfull + 32u;
+    const int my_items = (int)blockIdx.x < p.n_items ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    int t = 0;
+    for (int it = 0; it < my_items; ++it) {
+    float m_run = -INFINITY;  // (the running denominator lives in column d of the accumulator)
+    for (const int t_end = t + nkv; t < t_end; ++t) {
+      const int nvalid = (t == t_end - 1) ? last_valid : 64;
+      mbar_wait(b_sfull, (uint32_t)t & 1u);
       fence_after_sync();
       uint32_t sv[64];
       tmem_ld32_at<0>(tSp, sv);
@@ -815,22 +849,22 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mx = fmax3(mx, mx2, fmaxf(__uint_as_float(sv[62]), __uint_as_float(sv[63])));
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const bool grow = (m_new - m_run) > 8.f;  // (-inf) - (-inf) = NaN -> false: nothing to move
-      // P V_{j-1} of this half must be complete before O is touched or P overwritten
-      bool waited = (j == 0);
+      // P V of the CTA's previous tile (of this half) must be complete before O is touched or P overwritten
+      bool waited = (t == 0);
       if (DEFER == 0 && !waited) {
-        mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
+        mbar_wait(b_odone, (uint32_t)(t - 1) & 1u);
         fence_after_sync();
         waited = true;
       }
       if (__any_sync(0xffffffffu, grow)) {
         if (!waited) {
-          mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
+          mbar_wait(b_odone, (uint32_t)(t - 1) & 1u);
           fence_after_sync();
           waited = true;
         }
         const float alpha = grow ? ex2f(m_run - m_new) : 1.f;
         if (grow) m_run = m_new;
-        if (j > 0) {
+        if (t + nkv != t_end) {  // not the item's first tile: O holds partial sums
 #pragma unroll
           for (int c = 0; c < DV; c += 16) {
             uint32_t v[16];
@@ -879,7 +913,7 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
       for (int c = 0; c < DEFER; c += 8) early[c >> 3] = exp8(c);
       if (!waited) {
-        mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
+        mbar_wait(b_odone, (uint32_t)(t - 1) & 1u);
         fence_after_sync();
       }
       if (SETREG) {
@@ -899,12 +933,14 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       if (lane == 0) mbar_arrive(b_pfull);
     }
     // ---- merge the two halves of each row and write O / l as bf16 ----
-    float2* xch = reinterpret_cast<float2*>(gen + xch_off);
+    float2* xch = reinterpret_cast<float2*>(gen + xch_off) + (it & 1) * 256;
     if (h == 1) xch[g * 128 + row] = make_float2(m_run, 0.f);
     softmax_bar_sync();
     if (h == 0) {
-      mbar_wait(o_done(g, 0), (uint32_t)(nkv - 1) & 1u);
-      mbar_wait(o_done(g, 1), (uint32_t)(nkv - 1) & 1u);
+      int q0, head, b;
+      item_coords((int)blockIdx.x + it * (int)gridDim.x, q0, head, b);
+      mbar_wait(o_done(g, 0), (uint32_t)(t - 1) & 1u);
+      mbar_wait(o_done(g, 1), (uint32_t)(t - 1) & 1u);
       fence_after_sync();
       const float2 other = xch[g * 128 + row];
       const float m_all = fmaxf(m_run, other.x);
@@ -952,14 +988,19 @@ attn2h_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
         __syncwarp();
       }
+      // both accumulators of this row are in registers / on their way to HBM: the next item's first P V may overwrite them
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free(g));
     }
+    }  // items
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 16) tmem_dealloc(tmem, kTmemCols);
 }
 
-constexpr size_t attn2h_smem_bytes() { return 1024 + (size_t)(2 + 3 + 3 + 4) * 128 * 128 + 2048 + 8 + 8 * 12 + 96 + 8 * 3 + 16 + 16; }
+constexpr size_t attn2h_smem_bytes() { return 1024 + (size_t)(2 + 3 + 3 + 4) * 128 * 128 + 4096 + 8 + 8 * 12 + 96 + 8 * 3 + 24 + 16 + 16; }
 
 // ------------------------------------------------------------------------------------------------------
 // attn2x: the half-row design of attn2h for d = 80 (the 32x32 level).  Four accumulators of 96 columns (80 + the ones
@@ -1918,6 +1959,9 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
         // 0.754 ms for scalar code, 2, 3, 4 of 8; 0.679 / 0.617 / 0.639 / 0.703 for 2, 3, 4, 5 in the final kernel) and the first 16 keys' exponentials before the wait for P V_{j-1}
         // (0.625 / 0.617 / 0.645 / 0.682 ms for 8 / 16 / 24 / 32), profiles/r02_b_attn2h_packed_exp.log, r02_u_*.log.
         static const int setreg = getenv("SDTF_ATTN_SETREG") ? atoi(getenv("SDTF_ATTN_SETREG")) : 1;
+        static const int persist = getenv("SDTF_ATTN_PERSIST") ? atoi(getenv("SDTF_ATTN_PERSIST")) : 1;  // 0 (A/B): one item per CTA
+        p.heads = a.heads; p.n_qt = ceil_div(a.Nq, 256); p.n_items = p.n_qt * a.heads * a.B;
+        grid = dim3((unsigned)(persist && p.n_items > sm_count() ? sm_count() : p.n_items));
         const size_t sm = attn2h_smem_bytes();
         if (setreg) launch_pdl(attn2h_kernel<3, 48, 16, 3, true>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
         else launch_pdl(attn2h_kernel<3, 48, 16, 3>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);

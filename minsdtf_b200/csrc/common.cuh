@@ -155,6 +155,15 @@ inline CUtensorMap make_weight_tmap(const bf16* w, int K, int N, int taps, int B
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #endif
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    SDTF_CUDA(cudaGetDevice(&dev));
+    SDTF_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
 inline bool pdl_enabled() {
   static const int v = getenv("SDTF_PDL") ? atoi(getenv("SDTF_PDL")) : 0;
   return v != 0;

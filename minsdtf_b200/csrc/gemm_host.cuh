@@ -91,15 +91,6 @@ inline size_t conv_smem_bytes(int BN, int stages) {
   return 1024 + (size_t)stages * (kATileBytes + (size_t)BN * 128) + 8 * (2 * stages + 1) + 16;
 }
 
-inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    SDTF_CUDA(cudaGetDevice(&dev));
-    SDTF_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-  }
-  return n;
-}
 inline int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e && e[0]) ? atoi(e) : dflt;

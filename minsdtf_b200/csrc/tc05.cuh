@@ -70,6 +70,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Unbounded wait for threads that live on a small setmaxnreg budget (the watchdog above keeps a 64-bit start time, a poll
+// counter and the timer read alive across every wait: ~6 registers).  Their partners on the other side of the barrier
+// use the bounded wait, so a pipeline bug still ends in a trap.
+__device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / UMMA operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
