@@ -1959,9 +1959,11 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
         // 0.754 ms for scalar code, 2, 3, 4 of 8; 0.679 / 0.617 / 0.639 / 0.703 for 2, 3, 4, 5 in the final kernel) and the first 16 keys' exponentials before the wait for P V_{j-1}
         // (0.625 / 0.617 / 0.645 / 0.682 ms for 8 / 16 / 24 / 32), profiles/r02_b_attn2h_packed_exp.log, r02_u_*.log.
         static const int setreg = getenv("SDTF_ATTN_SETREG") ? atoi(getenv("SDTF_ATTN_SETREG")) : 1;
-        static const int persist = getenv("SDTF_ATTN_PERSIST") ? atoi(getenv("SDTF_ATTN_PERSIST")) : 1;  // 0 (A/B): one item per CTA
+        // SDTF_ATTN_PERSIST: 0 (A/B) = one item per CTA, N > 1 = at most N CTAs (sanitizer runs: several items per CTA at tiny sizes)
+        static const int persist = getenv("SDTF_ATTN_PERSIST") ? atoi(getenv("SDTF_ATTN_PERSIST")) : 1;
         p.heads = a.heads; p.n_qt = ceil_div(a.Nq, 256); p.n_items = p.n_qt * a.heads * a.B;
-        grid = dim3((unsigned)(persist && p.n_items > sm_count() ? sm_count() : p.n_items));
+        const int cap = persist > 1 ? persist : sm_count();
+        grid = dim3((unsigned)(persist && p.n_items > cap ? cap : p.n_items));
         const size_t sm = attn2h_smem_bytes();
         if (setreg) launch_pdl(attn2h_kernel<3, 48, 16, 3, true>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);
         else launch_pdl(attn2h_kernel<3, 48, 16, 3>, grid, dim3(kAHThreads), sm, stream, 1, tq, tk, tv, p);

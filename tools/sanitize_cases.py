@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One small launch of every hand-written pipeline kernel, for `compute-sanitizer --tool racecheck|synccheck|memcheck`
-(tools/gpu_sanitize.sh): attention variants (attn2h d=40 self, attn2q d=80 self, xattn d=40 / d=80 cross, attn d=160,
+(tools/gpu_sanitize.sh): attention variants (attn2h d=40 self, attn2x d=80 self, xattn d=40 / d=80 cross, attn d=160,
 vattn d=512), the one-kernel GroupNorm, LayerNorm, and the fused CFG + scheduler step.  Sizes are tiny: the sanitizer
 slows kernels by two orders of magnitude."""
 import os
@@ -18,7 +18,8 @@ def main():
     e = Engine(0)
     rng = np.random.default_rng(0)
     dl = _lib.DL()
-    for (B, nq, nk, heads, d) in [(1, 256, 256, 2, 40), (1, 256, 256, 2, 80), (1, 256, 77, 2, 40), (1, 256, 77, 2, 80), (1, 128, 128, 2, 160),
+    # (run with SDTF_ATTN_PERSIST=2: the (1, 768, 256, 2, 40) case is then 6 work items on 2 persistent CTAs)
+    for (B, nq, nk, heads, d) in [(1, 256, 256, 2, 40), (1, 768, 256, 2, 40), (1, 256, 256, 2, 80), (1, 256, 77, 2, 40), (1, 256, 77, 2, 80), (1, 128, 128, 2, 160),
                                   (1, 256, 256, 1, 512)]:
         q = rng.standard_normal((B, nq, heads * d)).astype(np.float32)
         k = rng.standard_normal((B, nk, heads * d)).astype(np.float32)
