@@ -1027,9 +1027,8 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const uint32_t sK = sQ + 2 * DCH * kChunk;         // KST x DCH chunks
   const uint32_t sV = sK + KST * DCH * kChunk;       // VST x DCH chunks
   const uint32_t sP = sV + VST * DCH * kChunk;       // chunk 2g+h = P of query tile g, key half h
-  // (the running maxima of the h = 1 threads cross to their h = 0 partners through the head of tile g's own Q chunks,
-  //  which nothing reads after that tile's last Q K^T)
-  const uint32_t bars = sP + 4 * kChunk;
+  const uint32_t xch_off = (sP - base) + 4 * kChunk;  // float [2][128]: running maxima of the h = 1 threads for the final merge
+  const uint32_t bars = base + xch_off + 1024u;
   const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u + 8u * s; };
   auto k_empty = [&](int s) { return bars + 24u + 8u * s; };
@@ -1042,18 +1041,27 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   auto s_taken = [&](int g) { return gbars + 16u + 8u * g; };
   auto p_full = [&](int g, int h) { return gbars + 32u + 8u * (2 * g + h); };
   auto o_done = [&](int g, int h) { return gbars + 64u + 8u * (2 * g + h); };
-  const uint32_t tmem_slot = gbars + 96u;
+  const uint32_t q_empty = gbars + 96u;  // every Q K^T of the item has completed: Q may be overwritten
+  auto o_free = [&](int g) { return gbars + 104u + 8u * g; };  // the merge has read tile g's accumulators
+  const uint32_t tmem_slot = gbars + 120u;
   uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen + (tmem_slot - base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, head = blockIdx.y, b = blockIdx.z;
   const int nkv = (p.Nk + 127) / 128;
+  // persistent CTAs as in attn2h: items = (batch, head, 256-query tile), barrier phases on the CTA-wide tile counter
+  auto item_coords = [&](int item, int& q0, int& head, int& b) {
+    const int qt = item % p.n_qt, hb = item / p.n_qt;
+    q0 = qt * 256; head = hb % p.heads; b = hb / p.heads;
+  };
+  const int my_items = (int)blockIdx.x < p.n_items ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   pdl_trigger();
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmQ); prefetch_tmap(&tmK); prefetch_tmap(&tmV);
     mbar_init(q_full, 1);
+    mbar_init(q_empty, 2);  // both tiles' MMA warps
+    for (int g = 0; g < 2; ++g) mbar_init(o_free(g), 4);  // the four h = 0 warps of the tile
     for (int s = 0; s < KST; ++s) { mbar_init(k_full(s), 1); mbar_init(k_empty(s), 2); }  // released by both tiles' MMA warps
     for (int s = 0; s < VST; ++s) { mbar_init(v_full(s), 1); mbar_init(v_empty(s), 2); mbar_init(v_ones(s), 1); }
     for (int g = 0; g < 2; ++g) {
@@ -1080,18 +1088,24 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // ===== TMA producer of Q and K =====
     setmaxnreg_dec<kCtlRegs>();
     if (elect_one()) {
-      mbar_expect_tx(q_full, 2 * DCH * kChunk);
+      int t = 0;
+      for (int it = 0; it < my_items; ++it) {
+        int q0, head, b;
+        item_coords((int)blockIdx.x + it * (int)gridDim.x, q0, head, b);
+        if (it > 0) mbar_wait(q_empty, (uint32_t)(it - 1) & 1u);
+        mbar_expect_tx(q_full, 2 * DCH * kChunk);
 #pragma unroll
-      for (int c = 0; c < DCH; ++c) {
-        tma_load_4d(sQ + c * kChunk, &tmQ, q_full, 64 * c, head, q0, b);
-        tma_load_4d(sQ + (DCH + c) * kChunk, &tmQ, q_full, 64 * c, head, q0 + 128, b);
-      }
-      for (int j = 0; j < nkv; ++j) {
-        const int ks = j % KST;
-        mbar_wait(k_empty(ks), ((uint32_t)(j / KST) & 1u) ^ 1u);
-        mbar_expect_tx(k_full(ks), DCH * kChunk);
+        for (int c = 0; c < DCH; ++c) {
+          tma_load_4d(sQ + c * kChunk, &tmQ, q_full, 64 * c, head, q0, b);
+          tma_load_4d(sQ + (DCH + c) * kChunk, &tmQ, q_full, 64 * c, head, q0 + 128, b);
+        }
+        for (int j = 0; j < nkv; ++j, ++t) {
+          const int ks = t % KST;
+          mbar_wait(k_empty(ks), ((uint32_t)(t / KST) & 1u) ^ 1u);
+          mbar_expect_tx(k_full(ks), DCH * kChunk);
 #pragma unroll
-        for (int c = 0; c < DCH; ++c) tma_load_4d(sK + (ks * DCH + c) * kChunk, &tmK, k_full(ks), 64 * c, head, j * 128, b);
+          for (int c = 0; c < DCH; ++c) tma_load_4d(sK + (ks * DCH + c) * kChunk, &tmK, k_full(ks), 64 * c, head, j * 128, b);
+        }
       }
     }
     __syncwarp();
@@ -1102,13 +1116,14 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       const int g = warp - 16;
       const uint32_t tS = tmem;  // shared by the two tiles
       const uint64_t dq = make_smem_desc_sw128(sQ + g * DCH * kChunk, 16, 1024);
-      auto issue_qk = [&](int j) {
-        const int st = j % KST;
-        mbar_wait(k_full(st), (uint32_t)(j / KST) & 1u);
-        // the S buffer is free once the OTHER tile's threads have pulled their scores: tile 1's S_{j-1} before tile 0's
-        // S_j, tile 0's S_j before tile 1's S_j
-        if (g == 0) { if (j > 0) mbar_wait(s_taken(1), (uint32_t)(j - 1) & 1u); }
-        else mbar_wait(s_taken(0), (uint32_t)j & 1u);
+      // tile t of the CTA = key tile j of the current item (this thread lives on 32 registers: unbounded waits, see attn2h)
+      auto issue_qk = [&](int t, int j) {
+        const int st = t % KST;
+        mbar_wait_lean(k_full(st), (uint32_t)(t / KST) & 1u);
+        // the S buffer is free once the OTHER tile's threads have pulled their scores: tile 1's previous S before tile 0's
+        // next one, tile 0's S_t before tile 1's S_t
+        if (g == 0) { if (t > 0) mbar_wait_lean(s_taken(1), (uint32_t)(t - 1) & 1u); }
+        else mbar_wait_lean(s_taken(0), (uint32_t)t & 1u);
         fence_after_sync();
         const uint32_t idesc = make_idesc_bf16(128, keys_in_tile(j), 0, 0);
         const uint64_t dk = make_smem_desc_sw128(sK + st * DCH * kChunk, 16, 1024);
@@ -1120,28 +1135,33 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         mma_commit(s_full(g));
         mma_commit(k_empty(st));
       };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
       const uint32_t idesc_pv = make_idesc_bf16(128, DV, 0, 1);  // B = V is MN-major
-      for (int j = 0; j < nkv; ++j) {
-        if (j + 1 < nkv) issue_qk(j + 1);
-        const int vs = j % VST;
-        mbar_wait(v_ones(vs), (uint32_t)(j / VST) & 1u);  // V tile landed and its ones column is in place
-        fence_after_sync();
-        const int ksteps = keys_in_tile(j) >> 4;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(p_full(g, h), (uint32_t)j & 1u);  // this half of P_j is in shared memory
+      int t = 0;
+      for (int it = 0; it < my_items; ++it) {
+        mbar_wait_lean(q_full, (uint32_t)it & 1u);
+        issue_qk(t, 0);
+        for (int j = 0; j < nkv; ++j, ++t) {
+          if (j + 1 < nkv) issue_qk(t + 1, j + 1);
+          else mma_commit(q_empty);  // arrives when every Q K^T of this item has completed
+          const int vs = t % VST;
+          mbar_wait_lean(v_ones(vs), (uint32_t)(t / VST) & 1u);  // V tile landed and its ones column is in place
+          if (j == 0 && it > 0) mbar_wait_lean(o_free(g), (uint32_t)(it - 1) & 1u);  // the previous item's merge has read O
           fence_after_sync();
-          const uint32_t tO = tmem + 128u + (uint32_t)(DV * (2 * g + h));
-          const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * g + h) * kChunk, 16, 1024);
-          for (int k = 4 * h; k < 4 * h + 4 && k < ksteps; ++k) {
-            const uint64_t db = make_smem_desc_sw128(sV + (uint32_t)(vs * DCH) * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
-            mma_f16_ss(tO, dp + 2 * (k & 3), db, idesc_pv, (j > 0) || (k > 4 * h));
+          const int ksteps = keys_in_tile(j) >> 4;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait_lean(p_full(g, h), (uint32_t)t & 1u);  // this half of P_j is in shared memory
+            fence_after_sync();
+            const uint32_t tO = tmem + 128u + (uint32_t)(DV * (2 * g + h));
+            const uint64_t dp = make_smem_desc_sw128(sP + (uint32_t)(2 * g + h) * kChunk, 16, 1024);
+            for (int k = 4 * h; k < 4 * h + 4 && k < ksteps; ++k) {
+              const uint64_t db = make_smem_desc_sw128(sV + (uint32_t)(vs * DCH) * kChunk + (uint32_t)k * 2048u, kChunk, 1024);
+              mma_f16_ss(tO, dp + 2 * (k & 3), db, idesc_pv, (j > 0) || (k > 4 * h));
+            }
+            mma_commit(o_done(g, h));
           }
-          mma_commit(o_done(g, h));
+          mma_commit(v_empty(vs));
         }
-        mma_commit(v_empty(vs));
       }
     }
     __syncwarp();
@@ -1150,16 +1170,19 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     // denominator (column d of O = sum_k P[q,k]) on the tensor core =====
     setmaxnreg_dec<kCtlRegs>();
     const uint32_t c64 = (uint32_t)p.d >> 6, chunk = ((uint32_t)(p.d & 63) * 2) >> 4, within = (uint32_t)(p.d * 2) & 15u;
-    auto load_v = [&](int t) {  // lane 0: V tile t into its ring slot, once P V of the slot's previous tenant has completed
+    const int n_tiles = my_items * nkv;
+    auto load_v = [&](int t) {  // lane 0: V tile t of the CTA into its ring slot, once P V of the slot's previous tenant has completed
       const int slot = t % VST;
+      int q0, head, b;
+      item_coords((int)blockIdx.x + (t / nkv) * (int)gridDim.x, q0, head, b);
       mbar_wait(v_empty(slot), ((uint32_t)(t / VST) & 1u) ^ 1u);
       mbar_expect_tx(v_full(slot), DCH * kChunk);
 #pragma unroll
-      for (int c = 0; c < DCH; ++c) tma_load_4d(sV + (slot * DCH + c) * kChunk, &tmV, v_full(slot), 64 * c, head, t * 128, b);
+      for (int c = 0; c < DCH; ++c) tma_load_4d(sV + (slot * DCH + c) * kChunk, &tmV, v_full(slot), 64 * c, head, (t % nkv) * 128, b);
     };
     if (lane == 0)
-      for (int t = 0; t < VST - 1 && t < nkv; ++t) load_v(t);
-    for (int j = 0; j < nkv; ++j) {
+      for (int t = 0; t < VST - 1 && t < n_tiles; ++t) load_v(t);
+    for (int j = 0; j < n_tiles; ++j) {
       if (VST == 1 && lane == 0) load_v(j);
       __syncwarp();
       const int vs = j % VST;
@@ -1172,7 +1195,7 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(v_ones(vs));
-        if (VST > 1 && j + VST - 1 < nkv) load_v(j + VST - 1);  // prefetch after the patch: the patch never waits for a P V
+        if (VST > 1 && j + VST - 1 < n_tiles) load_v(j + VST - 1);  // prefetch after the patch: the patch never waits for a P V
       }
       __syncwarp();
     }
@@ -1187,16 +1210,19 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int sw = row & 7;
     // 16-byte chunk c of this thread's P row sits at prow ^ (c << 4) (128-byte swizzle; bits 4-6 of the row start are 0)
     uint32_t prow = (sP + (uint32_t)(2 * g + h) * kChunk + (uint32_t)row * 128u) | ((uint32_t)sw << 4);
-    float m_run = -INFINITY;  // (the running denominator lives in column d of the accumulator)
     // loop-invariant addresses, pinned: ptxas otherwise rebuilds each of them from %tid and the shared window every tile
-    uint32_t b_sfull = s_full(g), b_staken = s_taken(g), b_pfull = p_full(g, h), b_odone = o_done(g, h), tSp = tS;
+    uint32_t b_sfull = s_full(g), b_pfull = p_full(g, h), tSp = tS;  // s_taken(g) = s_full(g) + 16, o_done(g, h) = p_full(g, h) + 32
     int last_valid = p.Nk - (nkv - 1) * 128 - 64 * h;  // valid keys of this half in the last tile (all others are full)
     last_valid = last_valid < 0 ? 0 : (last_valid > 64 ? 64 : last_valid);
-    pin_reg(b_sfull, lane); pin_reg(b_staken, lane); pin_reg(b_pfull, lane); pin_reg(b_odone, lane); pin_reg(tSp, lane);
+    pin_reg(b_sfull, lane); pin_reg(b_pfull, lane); pin_reg(tSp, lane);
     pin_reg(prow, lane);
-    for (int j = 0; j < nkv; ++j) {
-      const int nvalid = (j == nkv - 1) ? last_valid : 64;
-      mbar_wait(b_sfull, (uint32_t)j & 1u);
+    const uint32_t b_staken = b_sfull + 16u, b_odone = b_pfull + 32u;
+    int t = 0;
+    for (int it = 0; it < my_items; ++it) {
+    float m_run = -INFINITY;  // (the running denominator lives in column d of the accumulator)
+    for (const int t_end = t + nkv; t < t_end; ++t) {
+      const int nvalid = (t == t_end - 1) ? last_valid : 64;
+      mbar_wait(b_sfull, (uint32_t)t & 1u);
       fence_after_sync();
       uint32_t sv[64];
       tmem_ld32_at<0>(tSp, sv);
@@ -1220,16 +1246,16 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mx = fmax3(mx, mx2, fmaxf(__uint_as_float(sv[62]), __uint_as_float(sv[63])));
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const bool grow = (m_new - m_run) > 8.f;  // (-inf) - (-inf) = NaN -> false: nothing to move
-      bool waited = (j == 0);  // P V_{j-1} of this half must be complete before O is touched or P overwritten
+      bool waited = (t == 0);  // P V of the CTA's previous tile (this half) must be complete before O is touched or P overwritten
       if (__any_sync(0xffffffffu, grow)) {
         if (!waited) {
-          mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
+          mbar_wait(b_odone, (uint32_t)(t - 1) & 1u);
           fence_after_sync();
           waited = true;
         }
         const float alpha = grow ? ex2f(m_run - m_new) : 1.f;
         if (grow) m_run = m_new;
-        if (j > 0) {
+        if (t + nkv != t_end) {  // not the item's first tile: O holds partial sums
 #pragma unroll
           for (int c = 0; c < DV; c += 16) {
             uint32_t v[16];
@@ -1269,7 +1295,7 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       early[0] = exp8(0);
       early[1] = exp8(8);
       if (!waited) {
-        mbar_wait(b_odone, (uint32_t)(j - 1) & 1u);
+        mbar_wait(b_odone, (uint32_t)(t - 1) & 1u);
         fence_after_sync();
       }
       st_shared_v4(prow, early[0]);
@@ -1282,12 +1308,16 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       if (lane == 0) mbar_arrive(b_pfull);
     }
     // ---- merge the two halves of each row and write O / l as bf16 ----
-    float* xch = reinterpret_cast<float*>(gen + (sQ - base) + (uint32_t)(g * DCH) * kChunk);
+    // (one exchange buffer is enough: an h = 1 thread can finish the NEXT item only after its h = 0 partner has pulled that
+    //  item's first scores — the shared S buffer orders them — i.e. after the partner has read this item's entry; nkv >= 2)
+    float* xch = reinterpret_cast<float*>(gen + xch_off) + g * 128;
     if (h == 1) xch[row] = m_run;
     softmax_bar_sync();
     if (h == 0) {
-      mbar_wait(o_done(g, 0), (uint32_t)(nkv - 1) & 1u);
-      mbar_wait(o_done(g, 1), (uint32_t)(nkv - 1) & 1u);
+      int q0, head, b;
+      item_coords((int)blockIdx.x + it * (int)gridDim.x, q0, head, b);
+      mbar_wait(o_done(g, 0), (uint32_t)(t - 1) & 1u);
+      mbar_wait(o_done(g, 1), (uint32_t)(t - 1) & 1u);
       fence_after_sync();
       const float m_other = xch[row];
       const float m_all = fmaxf(m_run, m_other);
@@ -1335,7 +1365,12 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
         __syncwarp();
       }
+      // both accumulators of this row have been read: the next item's first P V may overwrite them
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_free(g));
     }
+    }  // items
   }
   fence_before_sync();
   __syncthreads();
@@ -1343,7 +1378,7 @@ attn2x_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 }
 
 template <int KST, int VST>
-constexpr size_t attn2x_smem_bytes() { return 1024 + (size_t)(4 + 2 * KST + 2 * VST + 4) * 128 * 128 + 88 + 96 + 16 + 16; }
+constexpr size_t attn2x_smem_bytes() { return 1024 + (size_t)(4 + 2 * KST + 2 * VST + 4) * 128 * 128 + 1024 + 88 + 96 + 24 + 16 + 16; }
 
 
 
@@ -1990,6 +2025,12 @@ inline void launch_attn(cudaStream_t stream, const AttnArgs& a) {
     } else {  // two query tiles per CTA, warp-specialised (softmax of one tile overlaps the MMAs of the other)
       dim3 grid((unsigned)ceil_div(a.Nq, 256), (unsigned)a.heads, (unsigned)a.B);
       static const int use_2x = getenv("SDTF_ATTN_2X") ? atoi(getenv("SDTF_ATTN_2X")) : 1;  // A/B: 0 = full-row kernel (round 1)
+      if (use_2x) {  // work items on a 1-D grid; persistent (SDTF_ATTN_PERSIST as for d = 40) when an item has >= 2 key tiles
+        static const int persist = getenv("SDTF_ATTN_PERSIST") ? atoi(getenv("SDTF_ATTN_PERSIST")) : 1;
+        p.heads = a.heads; p.n_qt = ceil_div(a.Nq, 256); p.n_items = p.n_qt * a.heads * a.B;
+        const int cap = persist > 1 ? persist : sm_count();
+        grid = dim3((unsigned)(persist && a.Nk > 128 && p.n_items > cap ? cap : p.n_items));
+      }
       if (use_2x == 2) launch_pdl(attn2x_kernel<5, 96, 3, 2, 1>, grid, dim3(kAHThreads), attn2x_smem_bytes<2, 1>(), stream, 1, tq, tk, tv, p);
       else if (use_2x) launch_pdl(attn2x_kernel<5, 96, 3, 1, 2>, grid, dim3(kAHThreads), attn2x_smem_bytes<1, 2>(), stream, 1, tq, tk, tv, p);
       else launch_pdl(attn2q_kernel<2, 5, 80, 2, 1>, grid, dim3(kA2Threads), attn2q_smem_bytes<2, 2, 1>(), stream, 1, tq, tk, tv, p);

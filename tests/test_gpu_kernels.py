@@ -32,6 +32,8 @@ def test_conv_gemm_standalone_cases():
     (1, 4096, 4096, 8, 40),    # 64x64 latent self-attention
     (3, 4096, 512, 8, 40),     # 384 work items on 148 persistent CTAs: two or three items per CTA
     (3, 4000, 500, 8, 40),     # ... ragged queries and keys
+    (5, 1024, 512, 8, 80),     # d = 80: 160 work items on 148 persistent CTAs
+    (5, 1000, 500, 8, 80),     # ... ragged
     (2, 1024, 1024, 8, 80),
     (2, 256, 256, 8, 160),
     (2, 64, 64, 8, 160),       # 8x8 mid block: fewer queries than a tile

@@ -19,7 +19,7 @@ def main():
     rng = np.random.default_rng(0)
     dl = _lib.DL()
     # (run with SDTF_ATTN_PERSIST=2: the (1, 768, 256, 2, 40) case is then 6 work items on 2 persistent CTAs)
-    for (B, nq, nk, heads, d) in [(1, 256, 256, 2, 40), (1, 768, 256, 2, 40), (1, 256, 256, 2, 80), (1, 256, 77, 2, 40), (1, 256, 77, 2, 80), (1, 128, 128, 2, 160),
+    for (B, nq, nk, heads, d) in [(1, 256, 256, 2, 40), (1, 768, 256, 2, 40), (1, 256, 256, 2, 80), (1, 768, 256, 2, 80), (1, 256, 77, 2, 40), (1, 256, 77, 2, 80), (1, 128, 128, 2, 160),
                                   (1, 256, 256, 1, 512)]:
         q = rng.standard_normal((B, nq, heads * d)).astype(np.float32)
         k = rng.standard_normal((B, nk, heads * d)).astype(np.float32)
