@@ -67,7 +67,8 @@ struct Gemm3Extra {
   int iters_split;       // k-iterations per range (the last range may be shorter)
   float* partial;        // split-K: fp32 partial sums [splits][B*H*W][N] (the reduce kernel applies the epilogue)
   long long* prof;       // optional [gridDim.x][16] cycle counters per role (null: off); see gemm_host.cuh
-  int debug;             // timing experiments only (results are garbage): 1 = skip the MMA instructions, 2 = skip the TMA loads
+  int debug;             // timing experiments only (results are garbage): 1 = skip the MMA instructions, 2 = skip the TMA loads,
+                         // 4 = no proxy fence after staging, 8 = no staging stores
   FastDiv d_ntiles, d_munits, d_tx, d_ty;  // divisors of the tile decode: n_tiles, ceil(m_tiles / CG), tiles_x, tiles_y
   int head_stride;       // > 0: output columns are heads of this many columns, tmOut is 5-D (make_epi_tmap_heads) and clips each head
 };
@@ -604,7 +605,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           o.y = pack_bf16(f[8 * c + 2], f[8 * c + 3]);
           o.z = pack_bf16(f[8 * c + 4], f[8 * c + 5]);
           o.w = pack_bf16(f[8 * c + 6], f[8 * c + 7]);
-          *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) = o;
+          if (!(x.debug & 8)) *reinterpret_cast<uint4*>(my_row + ((c ^ sw) << 4)) = o;
           if (ln_out) {  // statistics of what the consumer will read: the bf16-rounded values, summed in column order
             const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
@@ -623,7 +624,7 @@ conv_gemm3_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           ln_out[(long long)((n_tile * ncols + tc) >> 5) * p.ln_rows + ln_m] = make_float2(ln_s1, ln_s2);
         // (deferring this hand-over by one pass, so that the fence finds the stores long complete, was slower: with two
         //  staging buffers per set the later store delays the grant the set needs two passes on — 63.5 -> 68 us at 320 -> 1536)
-        fence_proxy_async_smem();  // staged row (generic proxy) -> visible to the TMA store (async proxy)
+        if (!(x.debug & 4)) fence_proxy_async_smem();  // staged row (generic proxy) -> visible to the TMA store (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(stg_bar(buf));
         if (prof_on) w_stage += clock64() - t_st0;
